@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI in include/hzb200.h (hanabizero_b200/csrc/libhzb200.so).
+
+There is no CPU fallback: if the library is missing the import of any product module fails with
+a build hint, and every non-zero status from the library raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libhzb200.so")
+
+HZ_OK, HZ_ERR_ARG, HZ_ERR_CUDA, HZ_ERR_STATE, HZ_ERR_ILLEGAL = 0, -1, -2, -3, -4
+
+
+class HzError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libhzb200 status {status}: {msg}")
+        self.status = status
+
+
+class IllegalMoveError(HzError, ValueError):
+    pass
+
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> (restype, argtypes); mirrors include/hzb200.h one to one (tests/test_abi.py checks that
+# every function the header declares is listed here and exported by the library)
+SIGNATURES = {
+    "hz_last_error": (C.c_char_p, []),
+    "hz_version": (_i, []),
+    "hz_launch_count": (_i64, []),
+    "hz_trees_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    "hz_trees_destroy": (_i, [_vp]),
+    "hz_trees_num": (_i, [_vp]),
+    "hz_trees_actions": (_i, [_vp]),
+    "hz_trees_capacity": (_i, [_vp]),
+    "hz_trees_prepare": (_i, [_vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "hz_trees_traverse": (_i, [_vp, _vp, _i, _f, _f, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "hz_trees_backprop": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp]),
+    "hz_trees_backprop_traverse": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp, _f, _i, _f,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "hz_trees_root_stats": (_i, [_vp, _vp, _vp, _vp]),
+    "hz_trees_trajectories": (_i, [_vp, _vp, _vp, _i]),
+    "hz_trees_export": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hz_gather_hidden": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "hz_envs_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp]),
+    "hz_envs_destroy": (_i, [_vp]),
+    "hz_envs_dims": (_i, [_vp, _vp]),
+    "hz_envs_reset": (_i, [_vp, _vp, _vp]),
+    "hz_envs_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hz_envs_observe": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "hz_envs_step_observe": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "hz_envs_check": (_i, [_vp, _vp, _vp]),
+    "hz_envs_dump": (_i, [_vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen libhzb200.so once and type every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m hanabizero_b200.build` "
+            "(nvcc, sm_100a). hanabizero_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [name for name in SIGNATURES if not hasattr(lib, name)]
+    if missing:
+        raise ImportError(f"{LIB_PATH} does not export {missing}: stale build, rerun "
+                          "`python -m hanabizero_b200.build --force`")
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status == HZ_OK:
+        return
+    msg = load().hz_last_error().decode("utf-8", "replace")
+    if status == HZ_ERR_ILLEGAL:
+        raise IllegalMoveError(status, msg)
+    raise HzError(status, msg)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count():
+    return int(load().hz_launch_count())

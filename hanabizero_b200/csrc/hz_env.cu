@@ -1,0 +1,667 @@
+// Batched Hanabi environment for sm_100a: one warp per game.
+//
+// Replaces, for the two presets the reference uses (rl_env.py:110-131, both 2-player, 5 ranks),
+// the C++ Hanabi Learning Environment behind libpyhanabi.so as sequenced by HanabiEnv.reset/step:
+//   rules     hanabi_state.cc:104-275 (ApplyMove, legality, fireworks, tokens, AdvanceToNextPlayer)
+//   hands     hanabi_hand.cc:80-126   (AddCard, RemoveFromHand, RevealColor/RevealRank knowledge)
+//   deals     hanabi_state.cc:277-325 + hanabi_game.cc:106-112: std::discrete_distribution over
+//             count/deck_size with the game's std::mt19937 (libstdc++ algorithm restated in fp64)
+//   observer  hanabi_observation.cc:52-96, encoder canonical_encoders.cc:66-486
+//   glue      rl_env.py:254-263,426-442 (global = own hand ‖ encoding ‖ turn; local; legal mask;
+//             reward = score delta; done)
+//
+// HBM layout: state [N][128] bytes (one 128-byte line per game, loaded as one word per lane into
+// shared memory), mt [N][624] uint32 + mti [N] (the game-owned Mersenne Twister, persists across
+// resets).  Observations are written lane-strided (coalesced) as float 0/1.  Scalar game logic is
+// executed by lane 0 on the shared-memory copy; the deal distribution (<= 25 outcomes), the
+// twister refill, legality and the 785/660-wide encodings are lane-parallel.
+#include "hz_common.cuh"
+
+namespace hz {
+
+constexpr int kEnvWarps = 4;
+constexpr int kStateBytes = 128;
+constexpr int P = 2;  // both reference presets are 2-player
+
+// byte offsets inside the 128-byte game state
+enum : int {
+  O_CUR = 0, O_NEXT = 1, O_INFO = 2, O_LIFE = 3, O_DECK = 4, O_TURNS = 5,
+  O_LMVALID = 6, O_LMTYPE = 7, O_LMPLAYER = 8, O_LMIDX = 9, O_LMTGT = 10, O_LMCOLOR = 11,
+  O_LMRANK = 12, O_LMCARD = 13, O_LMFLAGS = 14, O_LMREVEAL = 15,
+  O_FW = 16,       // [5]
+  O_HLEN = 21,     // [2]
+  O_DECKCNT = 24,  // [25]
+  O_DISC = 49,     // [25]
+  O_HAND = 74,     // [2][5][5] = {card, colour mask, rank mask, hinted colour, hinted rank}
+};
+enum : int { MV_PLAY = 1, MV_DISCARD = 2, MV_REVEAL_COLOR = 3, MV_REVEAL_RANK = 4 };  // hanabi_move.h:33
+constexpr uint8_t kNone = 0xff;
+
+struct Rules {
+  int C, R, H, max_info, max_life, A, enc_len, own_len, deck_max;
+};
+
+__device__ __forceinline__ int hand_off(int p, int k) { return O_HAND + (p * 5 + k) * 5; }
+__device__ __forceinline__ int instances(int rank, int R) { return rank == 0 ? 3 : (rank == R - 1 ? 1 : 2); }
+
+// ---- std::mt19937 (game-owned; hanabi_game.h:114) -------------------------------------------------
+__device__ __forceinline__ void mt_refill(uint32_t* mt, int lane) {
+  // in-place block update, 32 elements per pass: every element k needs old mt[k], old mt[k+1]
+  // (new mt[0] for k = 623) and mt[k+397 mod 624], which is old for k < 227 and was rewritten at
+  // least 7 passes earlier otherwise.  Reads of a pass complete before its writes.
+  for (int base = 0; base < 624; base += HZ_WARP) {
+    const int k = base + lane;
+    uint32_t v = 0;
+    if (k < 624) {
+      const uint32_t a = mt[k], b = mt[k == 623 ? 0 : k + 1], c = mt[k < 227 ? k + 397 : k - 227];
+      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      v = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+    if (k < 624) mt[k] = v;
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ uint32_t mt_draw(uint32_t* mt, int& mti, int lane) {
+  if (mti >= 624) {
+    mt_refill(mt, lane);
+    mti = 0;
+  }
+  uint32_t z = mt[mti++];
+  z ^= (z >> 11);
+  z ^= (z << 7) & 0x9d2c5680u;
+  z ^= (z << 15) & 0xefc60000u;
+  z ^= (z >> 18);
+  return z;
+}
+
+__device__ __forceinline__ double shfl_double(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(HZ_FULL, lo, src);
+  hi = __shfl_sync(HZ_FULL, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+__device__ __forceinline__ int player_to_deal(const uint8_t* st, int H) {  // hanabi_state.cc:157-164
+  if (st[O_HLEN] < H) return 0;
+  if (st[O_HLEN + 1] < H) return 1;
+  return -1;
+}
+
+__device__ __forceinline__ void advance(uint8_t* st, int H) {  // hanabi_state.cc:104-111
+  if (st[O_DECK] > 0 && player_to_deal(st, H) >= 0) {
+    st[O_CUR] = kNone;
+  } else {
+    st[O_CUR] = st[O_NEXT];
+    st[O_NEXT] = (uint8_t)((st[O_CUR] + 1) % P);
+  }
+}
+
+// ApplyRandomChance (hanabi_state.cc:282-286): ChanceOutcomes (313-325) -> PickRandomChance
+// (hanabi_game.cc:106-112, libstdc++ discrete_distribution + generate_canonical<double,53>) ->
+// ApplyMove(kDeal) (221-243).  Warp-cooperative; all lanes must call.
+__device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_t* mt, int& mti,
+                                            int lane) {
+  const int n_types = g.C * g.R;
+  const int cnt = lane < n_types ? st[O_DECKCNT + lane] : 0;
+  const bool have = cnt > 0;
+  const unsigned mask = __ballot_sync(HZ_FULL, have);
+  int pick = __ffs(mask) - 1;  // single outcome: _M_prob.size() < 2 -> index 0, no draw consumed
+  if (__popc(mask) >= 2) {
+    const double w = have ? __ddiv_rn((double)cnt, (double)st[O_DECK]) : 0.0;  // ChanceOutcomeProb
+    double sum = 0.0;  // std::accumulate ascending
+    for (unsigned m = mask; m; m &= m - 1) sum = __dadd_rn(sum, shfl_double(w, __ffs(m) - 1));
+    const double qn = have ? __ddiv_rn(w, sum) : 0.0;  // __normalize
+    double acc = 0.0, cp = 2.0;  // std::partial_sum ascending; lanes without an outcome never match
+    bool first = true;
+    const int last = 31 - __clz(mask);
+    for (unsigned m = mask; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      const double qv = shfl_double(qn, src);
+      acc = first ? qv : __dadd_rn(acc, qv);
+      first = false;
+      if (lane == src) cp = (src == last) ? 1.0 : acc;  // _M_cp.back() = 1.0
+    }
+    const uint32_t u0 = mt_draw(mt, mti, lane);
+    const uint32_t u1 = mt_draw(mt, mti, lane);
+    double p = __dadd_rn((double)u0, __dmul_rn((double)u1, 4294967296.0));
+    p = __dmul_rn(p, 5.421010862427522170037264004349708557128906250e-20);  // / 2^64 (exact)
+    if (p >= 1.0) p = 0x1.fffffffffffffp-1;                                // nextafter(1, 0)
+    const unsigned ge = __ballot_sync(HZ_FULL, have && cp >= p);           // std::lower_bound
+    pick = __ffs(ge) - 1;
+  }
+  if (lane == 0) {
+    const int to = player_to_deal(st, g.H);
+    const int k = st[O_HLEN + to]++;
+    const int o = hand_off(to, k);
+    st[o] = (uint8_t)pick;
+    st[o + 1] = (uint8_t)((1 << g.C) - 1);
+    st[o + 2] = (uint8_t)((1 << g.R) - 1);
+    st[o + 3] = kNone;
+    st[o + 4] = kNone;
+    st[O_DECKCNT + pick]--;
+    st[O_DECK]--;
+    advance(st, g.H);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ bool move_is_legal(const uint8_t* st, const Rules& g, int uid) {
+  // hanabi_state.cc:166-219 with the uid map of hanabi_game.cc:159-183
+  const int cur = (int8_t)st[O_CUR];
+  if (uid < 0 || uid >= g.A || cur < 0) return false;
+  const int H = g.H;
+  if (uid < H) return st[O_INFO] < g.max_info && uid < st[O_HLEN + cur];
+  uid -= H;
+  if (uid < H) return uid < st[O_HLEN + cur];
+  uid -= H;
+  if (st[O_INFO] == 0) return false;
+  const int t = (cur + 1) % P;  // target_offset is always 1 with two players
+  const int n = st[O_HLEN + t];
+  if (uid < g.C) {
+    for (int k = 0; k < n; ++k)
+      if (st[hand_off(t, k)] / g.R == uid) return true;
+    return false;
+  }
+  uid -= g.C;
+  for (int k = 0; k < n; ++k)
+    if (st[hand_off(t, k)] % g.R == uid) return true;
+  return false;
+}
+
+__device__ __forceinline__ void remove_from_hand(uint8_t* st, int p, int k) {  // hanabi_hand.cc:87-94
+  const int n = st[O_HLEN + p];
+  for (int j = k; j + 1 < n; ++j)
+    for (int f = 0; f < 5; ++f) st[hand_off(p, j) + f] = st[hand_off(p, j + 1) + f];
+  st[O_HLEN + p] = (uint8_t)(n - 1);
+}
+
+// HanabiState::ApplyMove for a player move (hanabi_state.cc:221-275); lane 0 only
+__device__ __forceinline__ void apply_move(uint8_t* st, const Rules& g, int uid) {
+  const int H = g.H, R = g.R, me = (int8_t)st[O_CUR];
+  if (st[O_DECK] == 0) st[O_TURNS]--;
+  st[O_LMVALID] = 1;
+  st[O_LMPLAYER] = (uint8_t)me;
+  st[O_LMIDX] = kNone; st[O_LMTGT] = kNone; st[O_LMCOLOR] = kNone; st[O_LMRANK] = kNone;
+  st[O_LMCARD] = kNone; st[O_LMFLAGS] = 0; st[O_LMREVEAL] = 0;
+  if (uid < H) {  // discard
+    st[O_LMTYPE] = MV_DISCARD;
+    st[O_LMIDX] = (uint8_t)uid;
+    if (st[O_INFO] < g.max_info) { st[O_INFO]++; st[O_LMFLAGS] |= 2; }
+    const int c = st[hand_off(me, uid)];
+    st[O_LMCARD] = (uint8_t)c;
+    st[O_DISC + c]++;
+    remove_from_hand(st, me, uid);
+  } else if (uid < 2 * H) {  // play
+    const int k = uid - H;
+    st[O_LMTYPE] = MV_PLAY;
+    st[O_LMIDX] = (uint8_t)k;
+    const int c = st[hand_off(me, k)], col = c / R, rk = c % R;
+    st[O_LMCARD] = (uint8_t)c;
+    if (rk == st[O_FW + col]) {  // AddToFireworks hanabi_state.cc:132-144
+      st[O_FW + col]++;
+      st[O_LMFLAGS] |= 1;
+      if (st[O_FW + col] == R && st[O_INFO] < g.max_info) { st[O_INFO]++; st[O_LMFLAGS] |= 2; }
+    } else {
+      st[O_LIFE]--;
+      st[O_DISC + c]++;
+    }
+    remove_from_hand(st, me, k);
+  } else {
+    const int t = (me + 1) % P;
+    const int n = st[O_HLEN + t];
+    st[O_LMTGT] = 1;
+    st[O_INFO]--;
+    uint8_t reveal = 0;
+    if (uid < 2 * H + g.C) {  // reveal colour (RevealColor hanabi_hand.cc:96-110)
+      const int col = uid - 2 * H;
+      st[O_LMTYPE] = MV_REVEAL_COLOR;
+      st[O_LMCOLOR] = (uint8_t)col;
+      for (int k = 0; k < n; ++k) {
+        const int o = hand_off(t, k);
+        if (st[o] / R == col) { reveal |= 1 << k; st[o + 3] = (uint8_t)col; st[o + 1] = (uint8_t)(1 << col); }
+        else st[o + 1] &= (uint8_t)~(1 << col);
+      }
+    } else {  // reveal rank (RevealRank hanabi_hand.cc:112-126)
+      const int rk = uid - 2 * H - g.C;
+      st[O_LMTYPE] = MV_REVEAL_RANK;
+      st[O_LMRANK] = (uint8_t)rk;
+      for (int k = 0; k < n; ++k) {
+        const int o = hand_off(t, k);
+        if (st[o] % R == rk) { reveal |= 1 << k; st[o + 4] = (uint8_t)rk; st[o + 2] = (uint8_t)(1 << rk); }
+        else st[o + 2] &= (uint8_t)~(1 << rk);
+      }
+    }
+    st[O_LMREVEAL] = reveal;
+  }
+  advance(st, H);
+}
+
+__device__ __forceinline__ int score_of(const uint8_t* st, int C) {  // hanabi_state.cc:359-364
+  if (st[O_LIFE] == 0) return 0;
+  int s = 0;
+  for (int c = 0; c < C; ++c) s += st[O_FW + c];
+  return s;
+}
+
+__device__ __forceinline__ bool is_terminal(const uint8_t* st, const Rules& g) {  // hanabi_state.cc:366-377
+  return st[O_LIFE] < 1 || score_of(st, g.C) >= g.C * g.R || (int8_t)st[O_TURNS] <= 0;
+}
+
+// HanabiState ctor (hanabi_state.cc:90-102) + HanabiDeck (53-64); lanes cooperate
+__device__ __forceinline__ void new_state(uint8_t* st, const Rules& g, int lane) {
+  for (int i = lane; i < kStateBytes; i += HZ_WARP) st[i] = 0;
+  __syncwarp();
+  if (lane < g.C * g.R) st[O_DECKCNT + lane] = (uint8_t)instances(lane % g.R, g.R);
+  if (lane == 0) {
+    st[O_CUR] = kNone;
+    st[O_NEXT] = 0;  // GetSampledStartPlayer with random_start_player = false
+    st[O_INFO] = (uint8_t)g.max_info;
+    st[O_LIFE] = (uint8_t)g.max_life;
+    st[O_DECK] = (uint8_t)g.deck_max;
+    st[O_TURNS] = P;
+  }
+  __syncwarp();
+}
+
+// bit i of CanonicalObservationEncoder::Encode (canonical_encoders.cc:441-463) for `obs`
+template <int C, int R, int H, int MI, int ML>
+__device__ __forceinline__ bool enc_bit(const uint8_t* st, int obs, int i) {
+  constexpr int BPC = C * R;
+  constexpr int PER_COLOR = 3 + 2 * (R - 2) + 1;
+  constexpr int DECK_MAX = PER_COLOR * C;
+  constexpr int HANDS = (P - 1) * H * BPC;
+  const int other = (obs + 1) % P;
+  // hands :66-109
+  if (i < HANDS) {
+    const int k = i / BPC, ci = i - k * BPC;
+    return k < st[O_HLEN + other] && st[hand_off(other, k)] == ci;
+  }
+  i -= HANDS;
+  if (i < P) return st[O_HLEN + (obs + i) % P] < H;
+  i -= P;
+  // board :127-171
+  constexpr int DW = DECK_MAX - P * H;
+  if (i < DW) return i < st[O_DECK];
+  i -= DW;
+  if (i < BPC) {
+    const int c = i / R, r = i - c * R;
+    return st[O_FW + c] == r + 1;
+  }
+  i -= BPC;
+  if (i < MI) return i < st[O_INFO];
+  i -= MI;
+  if (i < ML) return i < st[O_LIFE];
+  i -= ML;
+  // discards :192-215 (per colour: ranks with 3,2,..,2,1 copies, thermometer each)
+  if (i < DECK_MAX) {
+    const int c = i / PER_COLOR, w = i - c * PER_COLOR;
+    const int r = w < 3 ? 0 : (w - 3) / 2 + 1;
+    const int idx = w < 3 ? w : (w - 3) - (r - 1) * 2;
+    return idx < st[O_DISC + c * R + r];
+  }
+  i -= DECK_MAX;
+  // last action :240-342
+  constexpr int LAST = P + 4 + P + C + R + H + H + BPC + 2;
+  if (i < LAST) {
+    if (!st[O_LMVALID]) return false;
+    const int ty = st[O_LMTYPE];
+    const int rel = (st[O_LMPLAYER] - obs + P) % P;
+    const bool reveal = ty == MV_REVEAL_COLOR || ty == MV_REVEAL_RANK;
+    const bool pd = ty == MV_PLAY || ty == MV_DISCARD;
+    if (i < P) return i == rel;
+    i -= P;
+    if (i < 4) return i == (ty == MV_PLAY ? 0 : ty == MV_DISCARD ? 1 : ty == MV_REVEAL_COLOR ? 2 : 3);
+    i -= 4;
+    if (i < P) return reveal && i == (rel + st[O_LMTGT]) % P;
+    i -= P;
+    if (i < C) return ty == MV_REVEAL_COLOR && i == st[O_LMCOLOR];
+    i -= C;
+    if (i < R) return ty == MV_REVEAL_RANK && i == st[O_LMRANK];
+    i -= R;
+    if (i < H) return reveal && ((st[O_LMREVEAL] >> i) & 1);
+    i -= H;
+    if (i < H) return pd && i == st[O_LMIDX];
+    i -= H;
+    if (i < BPC) return pd && i == st[O_LMCARD];
+    i -= BPC;
+    return ty == MV_PLAY && ((st[O_LMFLAGS] >> i) & 1);
+  }
+  i -= LAST;
+  // card knowledge :370-423
+  constexpr int PER_CARD = BPC + C + R;
+  const int rel = i / (H * PER_CARD);
+  i -= rel * (H * PER_CARD);
+  const int k = i / PER_CARD, f = i - k * PER_CARD;
+  const int p = (obs + rel) % P;
+  if (k >= st[O_HLEN + p]) return false;
+  const int o = hand_off(p, k);
+  if (f < BPC) {
+    const int c = f / R, r = f - c * R;
+    return ((st[o + 1] >> c) & 1) && ((st[o + 2] >> r) & 1);
+  }
+  if (f < BPC + C) return st[o + 3] == f - BPC;
+  return st[o + 4] == f - BPC - C;
+}
+
+struct EnvView {
+  uint8_t* state;   // [N][128]
+  uint32_t* mt;     // [N][624]
+  int32_t* mti;     // [N]
+  int32_t* err;     // sticky: 1 + index of the first game that submitted an illegal move
+  int N;
+  Rules g;
+};
+
+struct EnvArgs {
+  const uint8_t* reset_mask;
+  const int32_t* actions;
+  const uint8_t* active;
+  int auto_reset;
+  int32_t* out_reward;
+  uint8_t* out_done;
+  int32_t* out_score;
+  float* out_global;
+  int64_t ld_global;
+  float* out_local;
+  int64_t ld_local;
+  float* out_legal;
+  int32_t* out_dump;
+};
+
+template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
+__global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs a) {
+  __shared__ uint32_t s_state[kEnvWarps][kStateBytes / 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gi = blockIdx.x * kEnvWarps + warp;
+  if (gi >= ev.N) return;
+  const Rules& g = ev.g;
+  uint8_t* st = reinterpret_cast<uint8_t*>(s_state[warp]);
+  uint32_t* gstate = reinterpret_cast<uint32_t*>(ev.state + (size_t)gi * kStateBytes);
+  uint32_t* mt = ev.mt + (size_t)gi * 624;
+  s_state[warp][lane] = gstate[lane];
+  int mti = ev.mti[gi];
+  const int mti0 = mti;
+  __syncwarp();
+  bool dirty = false;
+
+  if (RESET && (a.reset_mask == nullptr || a.reset_mask[gi])) {  // rl_env.py:249-252
+    new_state(st, g, lane);
+    while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, lane);
+    dirty = true;
+  }
+  if (STEP && (a.active == nullptr || a.active[gi])) {  // rl_env.py:413-438
+    const int action = a.actions[gi];
+    int reward = 0, done = 0, score = score_of(st, C);
+    if (!move_is_legal(st, g, action)) {  // reference: REQUIRE(MoveIsLegal) aborts the process
+      if (lane == 0) atomicCAS(ev.err, 0, gi + 1);
+      done = is_terminal(st, g);
+    } else {
+      const int last_score = score;
+      if (lane == 0) apply_move(st, g, action);
+      __syncwarp();
+      while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, lane);
+      score = score_of(st, C);
+      reward = score - last_score;
+      done = is_terminal(st, g);
+      dirty = true;
+      if (done && a.auto_reset) {
+        new_state(st, g, lane);
+        while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, lane);
+      }
+    }
+    if (lane == 0) {
+      if (a.out_reward) a.out_reward[gi] = reward;
+      if (a.out_done) a.out_done[gi] = (uint8_t)done;
+      if (a.out_score) a.out_score[gi] = score;
+    }
+  }
+  if (dirty) {
+    __syncwarp();
+    gstate[lane] = s_state[warp][lane];
+    if (lane == 0 && mti != mti0) ev.mti[gi] = mti;
+  }
+  if (OBSERVE) {
+    constexpr int BPC = C * R, OWN = H * BPC;
+    constexpr int ENC = ((P - 1) * H * BPC + P) + ((3 + 2 * (R - 2) + 1) * C - P * H + BPC + MI + ML) +
+                        (3 + 2 * (R - 2) + 1) * C + (P + 4 + P + C + R + H + H + BPC + 2) +
+                        P * H * (BPC + C + R);
+    constexpr int GLOBAL = OWN + ENC + P;
+    const int cur = (int8_t)st[O_CUR];
+    float* og = a.out_global ? a.out_global + (size_t)gi * a.ld_global : nullptr;
+    float* ol = a.out_local ? a.out_local + (size_t)gi * a.ld_local : nullptr;
+    for (int j = lane; j < GLOBAL; j += HZ_WARP) {
+      bool bit;
+      if (j < OWN) {  // EncodeOwnHand canonical_encoders.cc:465-486
+        const int k = j / BPC, ci = j - k * BPC;
+        bit = k < st[O_HLEN + cur] && st[hand_off(cur, k)] == ci;
+      } else if (j < OWN + ENC) {
+        bit = enc_bit<C, R, H, MI, ML>(st, cur, j - OWN);
+      } else {
+        bit = (j - OWN - ENC) == cur;  // agent_turn one-hot rl_env.py:256-257,429-430
+      }
+      const float v = bit ? 1.0f : 0.0f;
+      if (og) og[j] = v;
+      if (ol && j >= OWN) ol[j - OWN] = v;
+    }
+    if (a.out_legal && lane < g.A) {
+      a.out_legal[(size_t)gi * g.A + lane] = move_is_legal(st, g, lane) ? 1.0f : 0.0f;
+    }
+    if (a.out_dump && lane == 0) {  // layout of oracle/hanabi_oracle.c:ohanabi_dump
+      int32_t* o = a.out_dump + (size_t)gi * (5 + C + 2 * BPC + P * (1 + 5 * H));
+      int n = 0;
+      o[n++] = cur; o[n++] = st[O_INFO]; o[n++] = st[O_LIFE]; o[n++] = st[O_DECK];
+      o[n++] = is_terminal(st, g);
+      for (int c = 0; c < C; ++c) o[n++] = st[O_FW + c];
+      for (int i = 0; i < BPC; ++i) o[n++] = st[O_DECKCNT + i];
+      for (int i = 0; i < BPC; ++i) o[n++] = st[O_DISC + i];
+      for (int p = 0; p < P; ++p) {
+        o[n++] = st[O_HLEN + p];
+        for (int k = 0; k < H; ++k) {
+          const int ho = hand_off(p, k);
+          if (k < st[O_HLEN + p]) {
+            o[n++] = st[ho]; o[n++] = st[ho + 1]; o[n++] = st[ho + 2];
+            o[n++] = (int8_t)st[ho + 3]; o[n++] = (int8_t)st[ho + 4];
+          } else {
+            o[n++] = -1; o[n++] = 0; o[n++] = 0; o[n++] = -1; o[n++] = -1;
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void k_mt_seed(uint32_t* mt, int32_t* mti, const int32_t* seeds, int N) {
+  // std::mt19937::seed(value) (hanabi_game.cc:51): sequential recurrence, one thread per game
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= N) return;
+  uint32_t* m = mt + (size_t)gi * 624;
+  uint32_t x = (uint32_t)seeds[gi];
+  m[0] = x;
+  for (int i = 1; i < 624; ++i) {
+    x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+    m[i] = x;
+  }
+  mti[gi] = 624;
+}
+
+}  // namespace hz
+
+using namespace hz;
+
+struct hz_envs {
+  int device = 0, N = 0, preset = 0;
+  Rules g{};
+  uint8_t* state = nullptr;
+  uint32_t* mt = nullptr;
+  int32_t* mti = nullptr;
+  int32_t* err = nullptr;
+  bool started = false;
+  int dump_len = 0;
+  EnvView view() const { return EnvView{state, mt, mti, err, N, g}; }
+};
+
+template <bool RESET, bool STEP, bool OBSERVE>
+static int launch_env(hz_envs* e, cudaStream_t s, const EnvArgs& a) {
+  dim3 grid((e->N + kEnvWarps - 1) / kEnvWarps), block(kEnvWarps * HZ_WARP);
+  if (e->preset == 0) {
+    k_env<5, 5, 5, 8, 3, RESET, STEP, OBSERVE><<<grid, block, 0, s>>>(e->view(), a);
+  } else {
+    k_env<2, 5, 2, 3, 1, RESET, STEP, OBSERVE><<<grid, block, 0, s>>>(e->view(), a);
+  }
+  HZ_LAUNCH_CHECK("k_env");
+  return HZ_OK;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int hz_envs_create(hz_envs** out, int device, int num_games, int preset, const int32_t* seeds) {
+  if (!out || num_games <= 0 || (preset != 0 && preset != 1) || !seeds) {
+    set_error("hz_envs_create: need num_games>0, preset in {0,1}, host seeds[num_games]");
+    return HZ_ERR_ARG;
+  }
+  DeviceGuard dg(device);
+  if (!dg.ok) { set_error("hz_envs_create: cannot select device %d", device); return HZ_ERR_CUDA; }
+  hz_envs* e = new hz_envs;
+  e->device = device;
+  e->N = num_games;
+  e->preset = preset;
+  Rules& g = e->g;
+  if (preset == 0) { g.C = 5; g.R = 5; g.H = 5; g.max_info = 8; g.max_life = 3; }
+  else { g.C = 2; g.R = 5; g.H = 2; g.max_info = 3; g.max_life = 1; }
+  const int bpc = g.C * g.R, per_color = 3 + 2 * (g.R - 2) + 1;
+  g.deck_max = per_color * g.C;
+  g.A = 2 * g.H + (P - 1) * g.C + (P - 1) * g.R;
+  g.own_len = g.H * bpc;
+  g.enc_len = ((P - 1) * g.H * bpc + P) + (g.deck_max - P * g.H + bpc + g.max_info + g.max_life) +
+              g.deck_max + (P + 4 + P + g.C + g.R + g.H + g.H + bpc + 2) + P * g.H * (bpc + g.C + g.R);
+  e->dump_len = 5 + g.C + 2 * bpc + P * (1 + 5 * g.H);
+  const size_t n = (size_t)num_games;
+  int32_t* dseeds = nullptr;
+  cudaError_t err = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) { if (err == cudaSuccess) err = cudaMalloc(p, bytes); };
+  alloc((void**)&e->state, n * kStateBytes);
+  alloc((void**)&e->mt, n * 624 * sizeof(uint32_t));
+  alloc((void**)&e->mti, n * sizeof(int32_t));
+  alloc((void**)&e->err, sizeof(int32_t));
+  alloc((void**)&dseeds, n * sizeof(int32_t));
+  if (err == cudaSuccess) err = cudaMemset(e->state, 0, n * kStateBytes);
+  if (err == cudaSuccess) err = cudaMemset(e->err, 0, sizeof(int32_t));
+  if (err == cudaSuccess) err = cudaMemcpy(dseeds, seeds, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) {
+    k_mt_seed<<<(num_games + 127) / 128, 128>>>(e->mt, e->mti, dseeds, num_games);
+    g_launches.fetch_add(1);
+    err = cudaDeviceSynchronize();
+  }
+  cudaFree(dseeds);
+  if (err != cudaSuccess) {
+    hz_envs_destroy(e);
+    return fail_cuda(err, "hz_envs_create");
+  }
+  *out = e;
+  return HZ_OK;
+}
+
+int hz_envs_destroy(hz_envs* e) {
+  if (!e) return HZ_OK;
+  DeviceGuard dg(e->device);
+  cudaFree(e->state); cudaFree(e->mt); cudaFree(e->mti); cudaFree(e->err);
+  delete e;
+  return HZ_OK;
+}
+
+int hz_envs_dims(const hz_envs* e, int32_t* out) {
+  if (!e || !out) { set_error("hz_envs_dims: NULL argument"); return HZ_ERR_ARG; }
+  const Rules& g = e->g;
+  const int v[12] = {g.enc_len, g.own_len, P, g.A, g.C, g.R, g.H, g.max_info, g.max_life,
+                     g.enc_len + P, g.own_len + g.enc_len + P, e->dump_len};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return HZ_OK;
+}
+
+int hz_envs_reset(hz_envs* e, void* stream, const uint8_t* reset_mask) {
+  if (!e) { set_error("hz_envs_reset: NULL handle"); return HZ_ERR_ARG; }
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.reset_mask = reset_mask;
+  if (int rc = launch_env<true, false, false>(e, (cudaStream_t)stream, a)) return rc;
+  e->started = true;
+  return HZ_OK;
+}
+
+static int check_obs_args(const hz_envs* e, const float* og, int64_t ldg, const float* ol, int64_t ldl) {
+  if ((og && ldg < e->g.own_len + e->g.enc_len + P) || (ol && ldl < e->g.enc_len + P)) {
+    set_error("observation row stride smaller than the observation");
+    return HZ_ERR_ARG;
+  }
+  return HZ_OK;
+}
+
+int hz_envs_step(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active,
+                 int32_t* out_reward, uint8_t* out_done, int32_t* out_score) {
+  if (!e || !actions) { set_error("hz_envs_step: NULL argument"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_step: reset first"); return HZ_ERR_STATE; }
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.actions = actions; a.active = active;
+  a.out_reward = out_reward; a.out_done = out_done; a.out_score = out_score;
+  return launch_env<false, true, false>(e, (cudaStream_t)stream, a);
+}
+
+int hz_envs_observe(hz_envs* e, void* stream, float* out_global, int64_t ld_global,
+                    float* out_local, int64_t ld_local, float* out_legal) {
+  if (!e) { set_error("hz_envs_observe: NULL handle"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_observe: reset first"); return HZ_ERR_STATE; }
+  if (int rc = check_obs_args(e, out_global, ld_global, out_local, ld_local)) return rc;
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.out_global = out_global; a.ld_global = ld_global;
+  a.out_local = out_local; a.ld_local = ld_local; a.out_legal = out_legal;
+  return launch_env<false, false, true>(e, (cudaStream_t)stream, a);
+}
+
+int hz_envs_step_observe(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active,
+                         int auto_reset, int32_t* out_reward, uint8_t* out_done, int32_t* out_score,
+                         float* out_global, int64_t ld_global, float* out_local, int64_t ld_local,
+                         float* out_legal) {
+  if (!e || !actions) { set_error("hz_envs_step_observe: NULL argument"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_step_observe: reset first"); return HZ_ERR_STATE; }
+  if (int rc = check_obs_args(e, out_global, ld_global, out_local, ld_local)) return rc;
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.actions = actions; a.active = active; a.auto_reset = auto_reset;
+  a.out_reward = out_reward; a.out_done = out_done; a.out_score = out_score;
+  a.out_global = out_global; a.ld_global = ld_global;
+  a.out_local = out_local; a.ld_local = ld_local; a.out_legal = out_legal;
+  return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
+}
+
+int hz_envs_check(hz_envs* e, void* stream, int32_t* out_game) {
+  if (!e) { set_error("hz_envs_check: NULL handle"); return HZ_ERR_ARG; }
+  DeviceGuard dg(e->device);
+  int32_t v = 0;
+  HZ_CUDA(cudaMemcpyAsync(&v, e->err, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  HZ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (v != 0) {
+    HZ_CUDA(cudaMemsetAsync(e->err, 0, sizeof(v), (cudaStream_t)stream));
+    if (out_game) *out_game = v - 1;
+    set_error("illegal Hanabi move submitted by game %d (the reference aborts here: "
+              "REQUIRE(MoveIsLegal), hanabi_state.cc:222); the game was left untouched", v - 1);
+    return HZ_ERR_ILLEGAL;
+  }
+  return HZ_OK;
+}
+
+int hz_envs_dump(hz_envs* e, void* stream, int32_t* out) {
+  if (!e || !out) { set_error("hz_envs_dump: NULL argument"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_dump: reset first"); return HZ_ERR_STATE; }
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.out_dump = out;
+  return launch_env<false, false, true>(e, (cudaStream_t)stream, a);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,162 @@
+/* hzb200 — C ABI of the B200-native HanabiZero self-play hot path.
+ *
+ * One shared library (hanabizero_b200/csrc/libhzb200.so, sm_100a) replaces the two native
+ * libraries the reference binds on this path:
+ *   (1) the Cython extension `core.ctree.cytree` over core/ctree/{cnode,cminimax}.{h,cpp}
+ *       (/root/reference/core/ctree/cytree.pyx:17-101, ctree.pxd:9-77), and
+ *   (2) `libpyhanabi.so`, the cffi-loaded C API over envs/hanabi/hanabi_lib
+ *       (/root/reference/envs/hanabi/pyhanabi.h:24-195), as driven by HanabiEnv.reset/step
+ *       (/root/reference/envs/hanabi/rl_env.py:148-267, 292-442).
+ *
+ * Conventions: every function returns 0 on success and a negative hz_status on failure
+ * (hz_last_error() then holds a message, thread-local).  All `dev` pointers are device memory on
+ * the handle's device; `stream` is a cudaStream_t passed as void*.  No call synchronises the
+ * stream or allocates unless stated ("sync").  Batches are structure-of-arrays over trees/games;
+ * tree i / game i of a batch is the reference's roots[i] / envs[i].
+ */
+#ifndef HZB200_H
+#define HZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hz_trees hz_trees;
+typedef struct hz_envs hz_envs;
+
+typedef enum {
+  HZ_OK = 0,
+  HZ_ERR_ARG = -1,      /* bad argument (NULL handle, size mismatch, x out of capacity ...) */
+  HZ_ERR_CUDA = -2,     /* a CUDA runtime call or launch failed */
+  HZ_ERR_STATE = -3,    /* call order violated (backprop without traverse, step before reset ...) */
+  HZ_ERR_ILLEGAL = -4   /* an illegal Hanabi move was submitted (reference: REQUIRE -> abort,
+                           hanabi_state.cc:222) */
+} hz_status;
+
+const char* hz_last_error(void);
+int hz_version(void);
+/* number of kernels this library has launched in this process (bench.py "gpu_launches") */
+int64_t hz_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tree batch.  Replaces cytree.Roots + the per-tree node pools (CRoots, cnode.h:43-60;
+ * Roots.__cinit__, cytree.pyx:42-45) and the search paths held by ResultsWrapper/CSearchResults
+ * (cnode.h:62-73).  Capacity: `max_sims` expansions per tree beyond the root.
+ * ------------------------------------------------------------------------------------------ */
+int hz_trees_create(hz_trees** out, int device, int num_trees, int num_actions, int max_sims); /* sync */
+int hz_trees_destroy(hz_trees* t);                                                             /* sync */
+int hz_trees_num(const hz_trees* t);
+int hz_trees_actions(const hz_trees* t);
+int hz_trees_capacity(const hz_trees* t);
+
+/* CRoots::prepare / prepare_no_noise (cnode.cpp:247-259; cytree.pyx:47-51): masked softmax
+ * expansion of every root with hidden index (0, i), then the Dirichlet-noise mix.
+ * noises == NULL selects prepare_no_noise.  All inputs dev: noises/logits float[N][A],
+ * rewards float[N], masks int32[N][A] (0 = illegal).  Also discards any previous search. */
+int hz_trees_prepare(hz_trees* t, void* stream, float exploration_fraction, const float* noises,
+                     const float* rewards, const float* logits, const int32_t* masks);
+
+/* cmulti_traverse (cnode.cpp:407-441; cytree.multi_traverse, cytree.pyx:97-101) with the tie
+ * rule rand()==0.  minmax: dev float[N][2] = {minimum, maximum} per tree — the storage of
+ * CMinMaxStatsList (cminimax.h:13-36), owned by the caller like the reference's separate
+ * MinMaxStatsList object; value_delta_max is CMinMaxStats::value_delta_max.
+ * Outputs (dev, any may be NULL): out_ix/out_iy int32[N] = the leaf's PARENT hidden-state
+ * index, out_action int32[N] = last action, out_action64 int64[N] (same, for torch .long()).
+ * If pool != NULL, also gathers the parent hidden state rows (mcts.py:31-35 done on device):
+ *   out_hidden[i, :] = pool[(ix*N + iy) * row_bytes ...], row_bytes % 16 == 0. */
+int hz_trees_traverse(hz_trees* t, void* stream, int pb_c_base, float pb_c_init, float discount,
+                      const float* minmax, float value_delta_max, int32_t* out_ix, int32_t* out_iy,
+                      int32_t* out_action, int64_t* out_action64, const void* pool,
+                      void* out_hidden, int row_bytes);
+
+/* cmulti_back_propagate (cnode.cpp:337-344; cytree.multi_back_propagate, cytree.pyx:87-94):
+ * expand every leaf found by the last traverse with hidden index (hidden_state_index_x, i) and
+ * all-legal softmax priors, back-propagate `values` along the path, then refresh the per-tree
+ * min/max over all expanded non-root nodes (cback_propagate + update_tree_q, cnode.cpp:296-335).
+ * rewards/values float[N], logits float[N][A] (dev).  sanitize_nan != 0 zeroes NaN logits first
+ * (what core/mcts.py:48-49 does on the host).  minmax is written. */
+int hz_trees_backprop(hz_trees* t, void* stream, int hidden_state_index_x, float discount,
+                      const float* rewards, const float* values, const float* logits,
+                      int sanitize_nan, float* minmax);
+
+/* Fused step for the device-resident search loop: backprop of simulation k immediately followed
+ * by the traverse (+ gather) of simulation k+1 in ONE launch.  Same results as calling
+ * hz_trees_backprop then hz_trees_traverse. */
+int hz_trees_backprop_traverse(hz_trees* t, void* stream, int hidden_state_index_x, float discount,
+                               const float* rewards, const float* values, const float* logits,
+                               int sanitize_nan, float* minmax, float value_delta_max,
+                               int pb_c_base, float pb_c_init, int32_t* out_ix, int32_t* out_iy,
+                               int32_t* out_action, int64_t* out_action64, const void* pool,
+                               void* out_hidden, int row_bytes);
+
+/* CRoots::get_distributions / get_values (cnode.cpp:276-292): out_visits int32[N][A] (dev),
+ * out_values float[N] (dev). */
+int hz_trees_root_stats(hz_trees* t, void* stream, int32_t* out_visits, float* out_values);
+
+/* CRoots::get_trajectories (cnode.cpp:266-274): out int32[N][max_len] (dev), -1 padded. */
+int hz_trees_trajectories(hz_trees* t, void* stream, int32_t* out, int max_len);
+
+/* Test/inspection export: per tree and expansion index x in [1, cap]: reward, value_sum (dev
+ * float[N][cap]) and visit_count (dev int32[N][cap]); entries past the last expansion are 0.
+ * out_path_len int32[N] = length of the last search path (nodes incl. root). NULLs allowed. */
+int hz_trees_export(hz_trees* t, void* stream, int cap, float* out_reward, float* out_value_sum,
+                    int32_t* out_visits, float* out_root_priors, int32_t* out_path_len);
+
+/* mcts.py:31-35 as a standalone op: out[i,:] = pool[(ix[i]*num + iy[i]) * row_bytes ...]. */
+int hz_gather_hidden(void* stream, const void* pool, const int32_t* ix, const int32_t* iy,
+                     void* out, int num, int row_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Hanabi game batch.  Replaces, per game i, one HanabiGame + HanabiState + ObservationEncoder
+ * (pyhanabi.h: NewGame, NewState, StateApplyMove, StateDealRandomCard, NewObservation,
+ * EncodeObservation, EncodeOwnHandObservation, ObsGetLegalMove, StateScore,
+ * StateEndOfGameStatus) as sequenced by HanabiEnv.reset/step.
+ * preset: 0 = "Hanabi-Full", 1 = "Hanabi-Small" (rl_env.py:110-131).  seeds: HOST int32[N],
+ * game i seeds its own std::mt19937 with seeds[i] (hanabi_game.cc:43-51); the stream persists
+ * across resets like the reference's game object.
+ * ------------------------------------------------------------------------------------------ */
+int hz_envs_create(hz_envs** out, int device, int num_games, int preset, const int32_t* seeds); /* sync */
+int hz_envs_destroy(hz_envs* e);                                                                /* sync */
+/* dims: [enc_len, own_len, players, actions, colors, ranks, hand_size, max_info, max_life,
+ *        local_dim, global_dim, state_dump_len] */
+int hz_envs_dims(const hz_envs* e, int32_t* out12);
+
+/* HanabiEnv.reset (rl_env.py:148-267) for the games with reset_mask[i] != 0 (dev uint8[N];
+ * NULL = all games). Observations are produced by hz_envs_observe. */
+int hz_envs_reset(hz_envs* e, void* stream, const uint8_t* reset_mask);
+
+/* HanabiEnv.step (rl_env.py:292-442) for every game with active[i] != 0 (dev uint8[N]; NULL =
+ * all): apply move uid actions[i] (dev int32[N]), deal while chance, then reward = score delta,
+ * done, score.  out_reward/out_score int32[N], out_done uint8[N] (dev).  An illegal action
+ * leaves that game untouched and raises the sticky error flag read by hz_envs_check. */
+int hz_envs_step(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active,
+                 int32_t* out_reward, uint8_t* out_done, int32_t* out_score);
+
+/* The observation tuple HanabiEnv returns for the current player (rl_env.py:254-263, 426-434):
+ * out_global float[N][global_dim] = own-hand ‖ canonical encoding ‖ turn one-hot,
+ * out_local float[N][local_dim], out_legal float[N][actions] (dev; any may be NULL).
+ * ld_global/ld_local = row stride in elements (>= dim; lets the caller write straight into a
+ * frame-stack buffer). */
+int hz_envs_observe(hz_envs* e, void* stream, float* out_global, int64_t ld_global,
+                    float* out_local, int64_t ld_local, float* out_legal);
+
+/* step + auto-reset of finished games + observe in one launch (the self-play inner loop). */
+int hz_envs_step_observe(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active,
+                         int auto_reset, int32_t* out_reward, uint8_t* out_done, int32_t* out_score,
+                         float* out_global, int64_t ld_global, float* out_local, int64_t ld_local,
+                         float* out_legal);
+
+/* sync: returns HZ_ERR_ILLEGAL if any game saw an illegal action since the last check
+ * (out_game = first offending game index), clearing the flag. */
+int hz_envs_check(hz_envs* e, void* stream, int32_t* out_game);
+
+/* Full hidden state of every game for parity tests, int32[N][state_dump_len] (dev), layout of
+ * oracle/hanabi_oracle.c:ohanabi_dump. */
+int hz_envs_dump(hz_envs* e, void* stream, int32_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HZB200_H */

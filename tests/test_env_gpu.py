@@ -1,0 +1,160 @@
+"""GPU parity tests of the Hanabi kernels (through HanabiVecEnv / HanabiEnv -> C ABI) against golden
+episodes from the reference's own Python HanabiEnv and against the CPU oracle in lock step.
+Everything here is integer/bit work: the bar is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import env_policy, golden_files, load_golden, playable_from_dump, unpack_env_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_files("env_"))
+def test_cuda_replays_reference_python_env(name):
+    from gpu_adapters import GpuHanabiGame
+    g = load_golden(name)
+    glob_, loc = unpack_env_golden(g)
+    env = GpuHanabiGame(int(g["preset"]), int(g["seed"]))
+    starts = set(int(s) for s in g["ep_start"])
+    for t in range(len(g["action"])):
+        if t in starts:
+            go, lo, legal = env.reset()
+            r, d, sc = 0, False, 0
+        else:
+            go, lo, legal, r, d, sc = env.step(int(g["action"][t]))
+        assert (go == glob_[t]).all(), f"global obs differs at step {t}: bits {np.flatnonzero(go != glob_[t])[:10]}"
+        assert (lo == loc[t]).all(), f"local obs differs at step {t}"
+        assert (legal == g["legal"][t]).all(), f"legal mask differs at step {t}"
+        assert (r, int(d), sc) == (int(g["reward"][t]), int(g["done"][t]), int(g["score"][t])), t
+
+
+@pytest.mark.parametrize("preset", [0, 1])
+@pytest.mark.parametrize("mode", ["random", "noplay", "smart"])
+def test_batched_lockstep_vs_oracle(preset, mode):
+    """256 games with distinct seeds advance in one launch per step; every game is compared with its
+    own oracle instance: observations, legal masks, reward/done/score and the full hidden state.
+    Finished games are reset (same game object => the mt19937 stream continues)."""
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    from oracle import loader as L
+    N, T = 256, 260 if preset == 0 else 160
+    seeds = np.arange(N) * 3 + 100 * preset
+    vec = HanabiVecEnv(N, "Hanabi-Full" if preset == 0 else "Hanabi-Small", seeds)
+    cpus = [L.oracle_hanabi(preset, int(s)) for s in seeds]
+    rng = np.random.default_rng(5 + preset)
+    g, l, a = vec.reset_all()
+    g, l, a = g.cpu().numpy(), l.cpu().numpy(), a.cpu().numpy()
+    legal = []
+    for i, c in enumerate(cpus):
+        go, lo, lg = c.reset()
+        assert (go == g[i]).all() and (lo == l[i]).all() and (lg == a[i]).all(), i
+        legal.append(lg)
+    episodes = 0
+    for t in range(T):
+        dumps = vec.dump().cpu().numpy()
+        acts = np.zeros(N, np.int32)
+        for i, c in enumerate(cpus):
+            d = c.dump()
+            assert (d == dumps[i]).all(), (t, i)
+            acts[i] = env_policy(mode, rng, c.hand_size, legal[i], playable_from_dump(d, c.colors, c.ranks, c.hand_size))
+        g, l, a, r, dn, sc = vec.step_all(torch.from_numpy(acts).cuda())
+        vec.check()
+        g, l, a, r, dn, sc = (x.cpu().numpy() for x in (g, l, a, r, dn, sc))
+        reset_mask = np.zeros(N, np.uint8)
+        for i, c in enumerate(cpus):
+            go, lo, lg, rr, dd, ss = c.step(int(acts[i]))
+            assert (go == g[i]).all(), (t, i, np.flatnonzero(go != g[i])[:10])
+            assert (lo == l[i]).all() and (lg == a[i]).all(), (t, i)
+            assert (rr, int(dd), ss) == (int(r[i]), int(dn[i]), int(sc[i])), (t, i)
+            legal[i] = lg
+            if dd:
+                reset_mask[i] = 1
+        if reset_mask.any():
+            episodes += int(reset_mask.sum())
+            g, l, a = vec.reset_all(mask=torch.from_numpy(reset_mask).cuda())
+            g, l, a = g.cpu().numpy(), l.cpu().numpy(), a.cpu().numpy()
+            for i in np.flatnonzero(reset_mask):
+                go, lo, lg = cpus[i].reset()
+                assert (go == g[i]).all() and (lo == l[i]).all() and (lg == a[i]).all(), (t, i)
+                legal[i] = lg
+    assert episodes > N // 4
+
+
+def test_auto_reset_equals_explicit_reset():
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    N, T = 128, 120
+    seeds = np.arange(N) + 7
+    a_env, b_env = HanabiVecEnv(N, "Hanabi-Small", seeds), HanabiVecEnv(N, "Hanabi-Small", seeds)
+    ga, _, la = a_env.reset_all()
+    gb, _, lb = b_env.reset_all()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(T):
+        assert torch.equal(ga, gb) and torch.equal(la, lb)
+        acts = torch.multinomial(la + 1e-9, 1, generator=gen).view(-1).int()
+        ga, _, la, ra, da, sa = a_env.step_all(acts, auto_reset=True)
+        gb, _, lb, rb, db, sb = b_env.step_all(acts)
+        assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(sa, sb)
+        if db.any():
+            gb, _, lb = b_env.reset_all(mask=db.clone())
+    a_env.check(); b_env.check()
+
+
+def test_full_size_invariants_4096_games():
+    """BASELINE-size batch: 4096 Hanabi-Full games, random legal play with auto-reset; checks
+    domain invariants that do not need the oracle: card conservation, legal mask consistency,
+    observation bits in {0,1}, score/reward bookkeeping."""
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    N = 4096
+    vec = HanabiVecEnv(N, "Hanabi-Full", np.arange(N))
+    g, l, a = vec.reset_all()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    prev_score = torch.zeros(N, dtype=torch.int32, device="cuda")
+    for t in range(150):
+        assert ((g == 0) | (g == 1)).all() and (a.sum(1) > 0).all()
+        assert torch.equal(g[:, vec.own_len:], l)
+        acts = torch.multinomial(a, 1, generator=gen).view(-1).int()
+        g, l, a, r, d, s = vec.step_all(acts, auto_reset=True)
+        assert torch.equal(r, s - prev_score)
+        prev_score = torch.where(d.bool(), torch.zeros_like(s), s)
+        dump = vec.dump()
+        C, R, H = 5, 5, 5
+        deck = dump[:, 5 + C:5 + C + C * R].sum(1)
+        disc = dump[:, 5 + C + C * R:5 + C + 2 * C * R].sum(1)
+        fw = dump[:, 5:5 + C].sum(1)
+        base = 5 + C + 2 * C * R
+        hands = dump[:, base] + dump[:, base + 1 + 5 * H]
+        assert (deck == dump[:, 3]).all()
+        assert (deck + disc + fw + hands == 50).all(), "cards are conserved"
+    vec.check()
+
+
+def test_scalar_dropin_api_and_errors():
+    from hanabizero_b200.env_wrapper import HanabiControlWrapper
+    from hanabizero_b200.hanabi_env import HanabiEnv
+    from oracle import loader as L
+    env = HanabiEnv({"hanabi_name": "Hanabi-Full", "seed": None})
+    cpu = L.oracle_hanabi(0, 0)
+    assert env.players == 2 and env.action_space[0].n == 20 and env.num_moves() == 20
+    assert env.vectorized_observation_shape() == [658] and env.vectorized_share_observation_shape() == [783]
+    share, obs, legal = env.reset()
+    go, lo, lg = cpu.reset()
+    assert share == go.tolist() and obs == lo.tolist() and legal == lg.astype(float).tolist()
+    assert isinstance(share, list) and len(share) == 785 and len(obs) == 660 and len(legal) == 20
+    with pytest.raises(ValueError):
+        env.step(np.int64(5))                       # rl_env.py:415: only dict or int
+    with pytest.raises(ValueError):
+        env.step(int(np.flatnonzero(lg == 0)[0]))   # illegal uid: the reference aborts the process
+    a = int(np.flatnonzero(lg)[-1])
+    out = env.step(a)
+    ref = cpu.step(a)
+    assert out[0] == ref[0].tolist() and out[1] == ref[1].tolist() and out[5] == ref[2].astype(float).tolist()
+    assert (out[2], out[3], out[4]) == (ref[3], ref[4], {"score": ref[5]})
+    out = env.step({"action_type": "PLAY", "card_index": 0})
+    ref = cpu.step(5)
+    assert out[0] == ref[0].tolist() and out[2] == ref[3]
+    assert env.state.score() == ref[5] and env.state.cur_player() == int(cpu.dump()[0])
+    w = HanabiControlWrapper(HanabiEnv({"hanabi_name": "Hanabi-Small", "seed": 3}), discount=0.999, mdp="local")
+    o, lg2 = w.reset()
+    assert isinstance(o, np.ndarray) and o.shape == (173,) and lg2.shape == (11,)
+    o, r, d, info, lg2 = w.step(int(np.flatnonzero(lg2)[0]))
+    assert o.shape == (173,) and info.item()["score"] >= 0 and w.action_space_size == 11
