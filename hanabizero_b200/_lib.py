@@ -40,6 +40,7 @@ SIGNATURES = {
     "hz_trees_backprop": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp]),
     "hz_trees_backprop_traverse": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp, _f, _i, _f,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "hz_trees_set_progress": (_i, [_vp, _i]),
     "hz_trees_root_stats": (_i, [_vp, _vp, _vp, _vp]),
     "hz_trees_trajectories": (_i, [_vp, _vp, _vp, _i]),
     "hz_trees_export": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),

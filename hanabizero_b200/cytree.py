@@ -47,8 +47,8 @@ def as_device(x, dtype, device, shape=None):
         t = x.detach().to(device=device, dtype=dtype, non_blocking=True)
     else:
         np_dtype = {torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64,
-                    torch.uint8: np.uint8}[dtype]
-        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np_dtype)).to(device, non_blocking=True)
+                    torch.uint8: np.uint8}.get(dtype, np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np_dtype)).to(device=device, dtype=dtype)
     t = t.contiguous()
     if shape is not None:
         if t.numel() != int(np.prod(shape)):

@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing.  Trees and games are independent (cnode.cpp:415 touches tree i only; every
+game owns its RNG, hanabi_game.h:114), so the root / game batch is split into contiguous ranges,
+one process per GPU with a model replica, and the ONLY communication of a search is one
+all_gather of the final root statistics over NCCL (84 B per tree at A=20)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total, rank, world_size):
+    """Contiguous range [lo, hi) of trees/games owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(int(total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_root_stats(visits, values, group=None):
+    """all_gather of per-rank (visits int32 [n, A], values float32 [n]) -> global ([N, A], [N]) on every
+    rank, ranks in order.  Equal shard sizes use one all_gather_into_tensor on a packed buffer;
+    ragged shards fall back to all_gather on padded rows.  Works on NCCL (CUDA) and gloo (CPU)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return visits, values
+    world = dist.get_world_size(group)
+    n, a = visits.shape
+    packed = torch.empty(n, a + 1, dtype=torch.int32, device=visits.device)
+    packed[:, :a] = visits
+    packed[:, a] = values.contiguous().view(torch.int32)  # bit-cast: one collective for both
+    sizes = torch.tensor([n], dtype=torch.int64, device=visits.device)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [int(s.item()) for s in all_sizes]
+    if len(set(all_sizes)) == 1:
+        out = torch.empty(world * n, a + 1, dtype=torch.int32, device=visits.device)
+        dist.all_gather_into_tensor(out, packed, group=group)
+    else:
+        m = max(all_sizes)
+        pad = torch.zeros(m, a + 1, dtype=torch.int32, device=visits.device)
+        pad[:n] = packed
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        out = torch.cat([b[:k] for b, k in zip(bufs, all_sizes)])
+    return out[:, :a].contiguous(), out[:, a].contiguous().view(torch.float32)
+
+
+def gather_root_stats_equal(visits, values, out_packed, group=None):
+    """Sync-free variant for the timed path: equal shard sizes, caller-provided int32 [world*n, A+1]."""
+    n, a = visits.shape
+    packed = out_packed.new_empty(n, a + 1)
+    packed[:, :a] = visits
+    packed[:, a] = values.view(torch.int32)
+    dist.all_gather_into_tensor(out_packed, packed, group=group)
+    return out_packed[:, :a], out_packed[:, a].view(torch.float32)

@@ -1,0 +1,173 @@
+"""Search driver: drop-in for the reference's core/mcts.py (MCTS.run_multi, :7-57; `search` is
+the upstream-EfficientZero alias BASELINE.json uses).
+
+The reference loop crosses the host twice per simulation (Python-list marshalling into C++, a
+Python gather of hidden states, H2D of the batch, D2H + .tolist() of the network output).  Here a
+simulation is, on the device and on one stream:
+
+    [backprop of sim k-1 + traverse of sim k + gather of the parents' hidden states]  (1 launch)
+    -> model.recurrent_inference_device (PyTorch, cuBLAS)  -> next hidden state into pool[k]
+
+and the whole `num_simulations - 1` loop is captured in a CUDA graph after the first search with
+a given (tree handle, model, shape), so a search is one graph launch.  Exactly like the reference
+the last iteration is skipped (core/mcts.py:25-26): `num_simulations - 1` simulations run.
+
+Models: anything exposing `recurrent_inference_device(hidden, action) -> (value[N], reward[N],
+policy_logits[N, A], next_hidden[N, F])` on CUDA (hanabizero_b200.model does) gets the
+device-resident path.  A model with only the reference's `recurrent_inference` (numpy or tensor
+NetworkOutput) still works through the same kernels, paying that model's own host hops.
+"""
+import contextlib
+
+import numpy as np
+import torch
+
+from . import _lib, cytree
+from ._lib import check, ptr
+
+
+class SearchConfig:
+    """The hot-path constants of BaseMuZeroConfig (core/config.py:105-111) and the Hanabi configs
+    (config/hanabi_control/__init__.py:25-28,143-146) for callers without a reference config."""
+
+    def __init__(self, num_simulations=50, discount=0.999, value_delta_max=0.006, pb_c_base=19652,
+                 pb_c_init=1.25, amp_type="none", root_dirichlet_alpha=0.3,
+                 root_exploration_fraction=0.25):
+        self.num_simulations = num_simulations
+        self.discount = discount
+        self.value_delta_max = value_delta_max
+        self.pb_c_base = pb_c_base
+        self.pb_c_init = pb_c_init
+        self.amp_type = amp_type
+        self.root_dirichlet_alpha = root_dirichlet_alpha
+        self.root_exploration_fraction = root_exploration_fraction
+
+
+class _Workspace:
+    """Static device buffers of one (tree handle, model, shape): hidden-state pool [S, N, F], the
+    gathered batch handed to the model, the min/max statistics, and the captured graph."""
+
+    def __init__(self, roots, sims, feature, dtype):
+        n, dev = roots.root_num, roots.device
+        self.pool = torch.empty(sims, n, feature, dtype=dtype, device=dev)
+        self.hidden = torch.empty(n, feature, dtype=dtype, device=dev)
+        self.action64 = torch.zeros(n, 1, dtype=torch.int64, device=dev)
+        self.ix = torch.empty(n, dtype=torch.int32, device=dev)
+        self.la = torch.empty(n, dtype=torch.int32, device=dev)
+        self.minmax = cytree.MinMaxStatsList(n)
+        self.minmax.tensor(dev)
+        self.graph = None
+        self.searches = 0
+
+
+class MCTS(object):
+    max_cached_workspaces = 4
+
+    def __init__(self, config):
+        self.config = config
+        self._ws = {}
+
+    # ---------------------------------------------------------------------------------------------
+    def _autocast(self):
+        if getattr(self.config, "amp_type", "none") == "torch_amp":  # core/mcts.py:38-40
+            return torch.autocast("cuda", dtype=torch.float16)
+        return contextlib.nullcontext()
+
+    def _workspace(self, roots, model, hidden_state_roots):
+        sims = int(self.config.num_simulations)
+        key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"))
+        ws = self._ws.get(key)
+        if ws is None:
+            n, dev = roots.root_num, roots.device
+            feature = int(hidden_state_roots.shape[-1])
+            if hasattr(model, "recurrent_inference_device"):
+                with torch.no_grad(), self._autocast():
+                    probe = model.recurrent_inference_device(
+                        torch.zeros(2, feature, device=dev), torch.zeros(2, 1, dtype=torch.int64, device=dev))
+                dtype = probe[3].dtype
+            else:
+                dtype = torch.float32
+            if len(self._ws) >= self.max_cached_workspaces:
+                self._ws.pop(next(iter(self._ws)))
+            ws = self._ws[key] = _Workspace(roots, sims, feature, dtype)
+        return ws
+
+    def _simulate(self, roots, model, ws):
+        """The device-resident loop; everything is enqueued on the current stream (capturable)."""
+        cfg, lib, h = self.config, roots._lib, roots.handle
+        sims = int(cfg.num_simulations)
+        st = torch.cuda.current_stream(roots.device).cuda_stream
+        mm = ws.minmax
+        mm.set_delta(cfg.value_delta_max)
+        mm.clear()
+        mmp = ptr(mm.tensor(roots.device))
+        row_bytes = ws.hidden.shape[1] * ws.hidden.element_size()
+        base, init, disc, delta = int(cfg.pb_c_base), float(cfg.pb_c_init), float(cfg.discount), float(cfg.value_delta_max)
+        if sims < 2:
+            return
+        check(lib.hz_trees_traverse(h, st, base, init, disc, mmp, delta, ptr(ws.ix), None, ptr(ws.la),
+                                    ptr(ws.action64), ptr(ws.pool), ptr(ws.hidden), row_bytes))
+        for x in range(1, sims):
+            with self._autocast():
+                value, reward, logits, state = model.recurrent_inference_device(ws.hidden, ws.action64)
+            ws.pool[x].copy_(state)
+            value = value.float().contiguous()
+            reward = reward.float().contiguous()
+            logits = logits.float().contiguous()
+            if x < sims - 1:
+                check(lib.hz_trees_backprop_traverse(
+                    h, st, x, disc, ptr(reward), ptr(value), ptr(logits), 1, mmp, delta, base, init,
+                    ptr(ws.ix), None, ptr(ws.la), ptr(ws.action64), ptr(ws.pool), ptr(ws.hidden), row_bytes))
+            else:
+                check(lib.hz_trees_backprop(h, st, x, disc, ptr(reward), ptr(value), ptr(logits), 1, mmp))
+
+    def _simulate_compat(self, roots, model, ws):
+        """Same kernels around a model that only speaks the reference's NetworkOutput contract."""
+        cfg = self.config
+        sims = int(cfg.num_simulations)
+        mm = ws.minmax
+        mm.set_delta(cfg.value_delta_max)
+        mm.clear()
+        for x in range(1, sims):
+            results = cytree.ResultsWrapper(roots.root_num)
+            cytree.multi_traverse(roots, cfg.pb_c_base, cfg.pb_c_init, cfg.discount, mm, results,
+                                  as_tensor=True, pool=ws.pool, out_hidden=ws.hidden, out_action64=ws.action64)
+            with self._autocast():
+                out = model.recurrent_inference(ws.hidden.float(), ws.action64)
+            dev = roots.device
+            ws.pool[x].copy_(cytree.as_device(out.hidden_state, ws.pool.dtype, dev))
+            cytree.multi_back_propagate(x, cfg.discount, _flat(out.reward), _flat(out.value),
+                                        out.policy_logits, mm, results, sanitize_nan=True)
+
+    # ---------------------------------------------------------------------------------------------
+    def run_multi(self, roots, model, hidden_state_roots, use_graph=True):
+        """core/mcts.py:11-57.  roots: cytree.Roots already prepared; hidden_state_roots: [N, F]
+        numpy array or tensor (any device).  Mutates `roots` in place and returns None."""
+        with torch.no_grad():
+            model.eval()
+            ws = self._workspace(roots, model, hidden_state_roots)
+            ws.pool[0].copy_(cytree.as_device(hidden_state_roots, ws.pool.dtype, roots.device))
+            sims = int(self.config.num_simulations)
+            if not hasattr(model, "recurrent_inference_device"):
+                self._simulate_compat(roots, model, ws)
+            elif not use_graph:
+                self._simulate(roots, model, ws)
+            elif ws.graph is None and ws.searches == 0:
+                self._simulate(roots, model, ws)  # first search runs eagerly (also warms cuBLAS)
+            else:
+                if ws.graph is None:
+                    torch.cuda.synchronize(roots.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._simulate(roots, model, ws)
+                    ws.graph = graph
+                ws.graph.replay()
+                # host-side progress of the handle is not touched by a replay
+                check(roots._lib.hz_trees_set_progress(roots.handle, max(sims - 1, 0)))
+            ws.searches += 1
+
+    search = run_multi  # upstream EfficientZero name (BASELINE.json north_star)
+
+
+def _flat(x):
+    return x.reshape(-1) if isinstance(x, torch.Tensor) else np.asarray(x).reshape(-1)

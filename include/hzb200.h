@@ -91,6 +91,11 @@ int hz_trees_backprop_traverse(hz_trees* t, void* stream, int hidden_state_index
                                int32_t* out_action, int64_t* out_action64, const void* pool,
                                void* out_hidden, int row_bytes);
 
+/* After replaying a CUDA graph that contains the calls above, the handle's host-side progress
+ * (number of completed back-propagations since prepare) must be restored by hand: a replay runs
+ * the kernels but not the host code.  expansions in [0, capacity]. */
+int hz_trees_set_progress(hz_trees* t, int expansions);
+
 /* CRoots::get_distributions / get_values (cnode.cpp:276-292): out_visits int32[N][A] (dev),
  * out_values float[N] (dev). */
 int hz_trees_root_stats(hz_trees* t, void* stream, int32_t* out_visits, float* out_values);
