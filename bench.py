@@ -370,6 +370,8 @@ def run_ours(args):
     e1.record()
     barrier()
     env_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    h_leg.copy_(legal); torch.cuda.synchronize()
+    h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
     env_pass(5, True)
     barrier()
     e0.record()

@@ -31,7 +31,8 @@ def _record(model):
 
     def wrapped(h, act):
         out = orig(h, act)
-        rec.append(tuple(o.detach().clone() for o in out[:3]) + (h.detach().clone(), act.detach().clone()))
+        if h.shape[0] == N:   # skip the 2-row dtype probe MCTS makes when it builds its workspace
+            rec.append(tuple(o.detach().clone() for o in out[:3]) + (h.detach().clone(), act.detach().clone()))
         return out
 
     model.recurrent_inference_device = wrapped
