@@ -63,8 +63,9 @@ class _Workspace:
 class MCTS(object):
     max_cached_workspaces = 4
 
-    def __init__(self, config):
+    def __init__(self, config, use_plan=True):
         self.config = config
+        self.use_plan = use_plan
         self._ws = {}
 
     # ---------------------------------------------------------------------------------------------
@@ -73,14 +74,23 @@ class MCTS(object):
             return torch.autocast("cuda", dtype=torch.float16)
         return contextlib.nullcontext()
 
+    def _plan(self, model):
+        """The model's fused eval-mode plan (hanabizero_b200/plan.py) if it offers one and use_plan is on."""
+        if not self.use_plan or not hasattr(model, "recurrent_plan"):
+            return None
+        amp = getattr(self.config, "amp_type", "none") == "torch_amp"
+        return model.recurrent_plan(torch.float16 if amp else torch.float32)
+
     def _workspace(self, roots, model, hidden_state_roots):
         sims = int(self.config.num_simulations)
-        key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"))
+        key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"), self.use_plan)
         ws = self._ws.get(key)
         if ws is None:
             n, dev = roots.root_num, roots.device
             feature = int(hidden_state_roots.shape[-1])
-            if hasattr(model, "recurrent_inference_device"):
+            if self._plan(model) is not None:
+                dtype = self._plan(model).dtype
+            elif hasattr(model, "recurrent_inference_device"):
                 with torch.no_grad(), self._autocast():
                     probe = model.recurrent_inference_device(
                         torch.zeros(2, feature, device=dev), torch.zeros(2, 1, dtype=torch.int64, device=dev))
@@ -107,13 +117,17 @@ class MCTS(object):
             return
         check(lib.hz_trees_traverse(h, st, base, init, disc, mmp, delta, ptr(ws.ix), None, ptr(ws.la),
                                     ptr(ws.action64), ptr(ws.pool), ptr(ws.hidden), row_bytes))
+        plan = self._plan(model)
         for x in range(1, sims):
-            with self._autocast():
-                value, reward, logits, state = model.recurrent_inference_device(ws.hidden, ws.action64)
-            ws.pool[x].copy_(state)
-            value = value.float().contiguous()
-            reward = reward.float().contiguous()
-            logits = logits.float().contiguous()
+            if plan is not None:   # next hidden state is written straight into its pool slot
+                value, reward, logits = plan.run(ws.hidden, ws.action64, ws.pool[x])
+            else:
+                with self._autocast():
+                    value, reward, logits, state = model.recurrent_inference_device(ws.hidden, ws.action64)
+                ws.pool[x].copy_(state)
+                value = value.float().contiguous()
+                reward = reward.float().contiguous()
+                logits = logits.float().contiguous()
             if x < sims - 1:
                 check(lib.hz_trees_backprop_traverse(
                     h, st, x, disc, ptr(reward), ptr(value), ptr(logits), 1, mmp, delta, base, init,
@@ -146,6 +160,8 @@ class MCTS(object):
         with torch.no_grad():
             model.eval()
             ws = self._workspace(roots, model, hidden_state_roots)
+            if self._plan(model) is not None:
+                self._plan(model).refresh()   # re-fold weights in place if the module was updated
             ws.pool[0].copy_(cytree.as_device(hidden_state_roots, ws.pool.dtype, roots.device))
             sims = int(self.config.num_simulations)
             if not hasattr(model, "recurrent_inference_device"):

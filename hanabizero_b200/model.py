@@ -169,6 +169,15 @@ class HanabiMuZeroNet(nn.Module):
         return (self.inverse_scalar_transform(value, self._value_support),
                 self.inverse_scalar_transform(reward, self._reward_support), logits.float(), state)
 
+    def recurrent_plan(self, dtype=torch.float32):
+        """Folded/fused execution plan of recurrent_inference for eval mode (hanabizero_b200/plan.py),
+        cached per dtype; call plan.refresh() (cheap, automatic in MCTS.run_multi) after weight updates."""
+        from .plan import RecurrentPlan
+        plans = self.__dict__.setdefault("_plans", {})
+        if dtype not in plans:
+            plans[dtype] = RecurrentPlan(self, dtype)
+        return plans[dtype]
+
     # -- the reference's contract (core/model.py:61-84): numpy on the host in eval mode --------------------
     def initial_inference(self, obs):
         if self.training:

@@ -161,6 +161,23 @@ int hz_envs_check(hz_envs* e, void* stream, int32_t* out_game);
  * oracle/hanabi_oracle.c:ohanabi_dump. */
 int hz_envs_dump(hz_envs* e, void* stream, int32_t* out);
 
+/* ------------------------------------------------------------------------------------------
+ * Glue around the PyTorch network (the GEMMs stay cuBLAS): keeps value/reward decoding and the
+ * layer epilogues on the device in one launch each.
+ * ------------------------------------------------------------------------------------------ */
+/* inverse_scalar_transform (/root/reference/core/config.py:210-232): per row softmax over `width`
+ * support bins (logits dev, elem_bytes 4 = float / 2 = half, row stride ld elements), expectation
+ * against support[width] (dev float), / delta, inverse of h(x)=sign(x)(sqrt(|x|+1)-1)+0.001x,
+ * NaN -> 0.  out: dev float[rows]. */
+int hz_support_decode(void* stream, const void* logits, int elem_bytes, const float* support,
+                      float* out, int rows, int width, int64_t ld, float delta);
+/* GEMM epilogue: out[r][c] = act(x[r][c] + bias[c] + residual[r][c] + table[idx[r]][c]); bias,
+ * residual and table (+ int64 idx[rows]) are optional (NULL); relu != 0 applies max(.,0).
+ * All matrices dev, element type by elem_bytes (4 float / 2 half), row strides in elements. */
+int hz_bias_act(void* stream, void* out, int64_t ld_out, const void* x, int64_t ld_x, const void* bias,
+                const void* residual, int64_t ld_res, const void* table, const int64_t* idx,
+                int rows, int cols, int relu, int elem_bytes);
+
 #ifdef __cplusplus
 }
 #endif

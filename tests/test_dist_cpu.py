@@ -1,0 +1,52 @@
+"""CPU, world_size 2 over gloo: the multi-GPU host logic — contiguous root sharding and the single
+all_gather of final root statistics (the only communication of a search)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hanabizero_b200.dist import gather_root_stats, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for total in (1, 7, 4096, 16384, 1001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, total, A, ragged, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)
+    visits_all = rng.integers(0, 50, (total, A)).astype(np.int32)
+    values_all = rng.standard_normal(total).astype(np.float32)
+    lo, hi = shard_range(total, rank, world)
+    v, val = gather_root_stats(torch.from_numpy(visits_all[lo:hi]), torch.from_numpy(values_all[lo:hi]))
+    ok = bool((v.numpy() == visits_all).all() and (val.numpy().view(np.uint32) == values_all.view(np.uint32)).all())
+    out_q.put((rank, ok, tuple(v.shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total,ragged", [(64, False), (37, True)])
+def test_gather_root_stats_world2_gloo(total, ragged):
+    world, A = 2, 20
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (1 if ragged else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, A, ragged, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, shape in res:
+        assert ok and shape == (total, A), (rank, ok, shape)

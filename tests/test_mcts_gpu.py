@@ -25,14 +25,26 @@ def _setup(amp="none", small=False):
     return dev, model, logits, hidden, legal, noise, SearchConfig(num_simulations=S, amp_type=amp), a
 
 
-def _record(model):
+def _record(model, plan=None):
+    """Record (value, reward, logits, hidden_in, action_in, next_state) of every network call made by
+    the search, on the nn.Module path or on the fused-plan path."""
     rec = []
+    if plan is not None:
+        orig = plan.run
+
+        def wrapped_plan(h, act, out_state):
+            v, r, lg = orig(h, act, out_state)
+            rec.append((v.clone(), r.clone(), lg.clone(), h.detach().clone(), act.detach().clone(), out_state.clone()))
+            return v, r, lg
+
+        plan.run = wrapped_plan
+        return rec, orig
     orig = model.recurrent_inference_device
 
     def wrapped(h, act):
         out = orig(h, act)
         if h.shape[0] == N:   # skip the 2-row dtype probe MCTS makes when it builds its workspace
-            rec.append(tuple(o.detach().clone() for o in out[:3]) + (h.detach().clone(), act.detach().clone()))
+            rec.append(tuple(o.detach().clone() for o in out[:3]) + (h.detach().clone(), act.detach().clone(), out[3].clone()))
         return out
 
     model.recurrent_inference_device = wrapped
@@ -44,23 +56,28 @@ def _oracle_replay(rec, cfg, noise, logits, legal, a):
     cpu = L.oracle_tree(N, a, S, cfg.value_delta_max)
     cpu.prepare(0.25, noise, np.zeros(N, np.float32), logits.float().cpu().numpy(), legal.cpu().numpy().astype(np.int32))
     trace = []
-    for x, (v, rw, lg, _, _) in enumerate(rec, start=1):
+    for x, (v, rw, lg, _, _, _) in enumerate(rec, start=1):
         trace.append(cpu.traverse(cfg.pb_c_base, cfg.pb_c_init, cfg.discount))
         cpu.backprop(x, cfg.discount, rw.float().cpu().numpy(), v.float().cpu().numpy(),
                      np.nan_to_num(lg.float().cpu().numpy(), nan=0.0))
     return cpu, trace
 
 
+@pytest.mark.parametrize("use_plan", [True, False])
 @pytest.mark.parametrize("amp,small", [("none", False), ("torch_amp", False), ("none", True)])
-def test_run_multi_matches_oracle_given_same_network_outputs(amp, small):
+def test_run_multi_matches_oracle_given_same_network_outputs(amp, small, use_plan):
     from hanabizero_b200 import cytree
     from hanabizero_b200.mcts import MCTS
     dev, model, logits, hidden, legal, noise, cfg, a = _setup(amp, small)
-    rec, orig = _record(model)
+    plan = model.recurrent_plan(torch.float16 if amp == "torch_amp" else torch.float32) if use_plan else None
+    rec, orig = _record(model, plan)
     roots = cytree.Roots(N, a, S)
     roots.prepare(0.25, noise, [0.0] * N, logits, legal)
-    MCTS(cfg).run_multi(roots, model, hidden, use_graph=False)
-    model.recurrent_inference_device = orig
+    MCTS(cfg, use_plan=use_plan).run_multi(roots, model, hidden, use_graph=False)
+    if use_plan:
+        plan.run = orig
+    else:
+        model.recurrent_inference_device = orig
     assert len(rec) == S - 1                               # the last iteration is skipped (core/mcts.py:25-26)
     cpu, trace = _oracle_replay(rec, cfg, noise, logits, legal, a)
     visits, values = roots.get_stats_tensors()
@@ -69,12 +86,11 @@ def test_run_multi_matches_oracle_given_same_network_outputs(amp, small):
     np.testing.assert_allclose(values.cpu().numpy(), oval, rtol=1e-5)
     # the batches handed to the network are the parents' hidden states and the last actions
     pool = [hidden.to(rec[0][3].dtype)] + [None] * S
-    for x, ((v, rw, lg, h, act), (ix, iy, la)) in enumerate(zip(rec, trace), start=1):
+    for x, ((v, rw, lg, h, act, nxt), (ix, iy, la)) in enumerate(zip(rec, trace), start=1):
         assert (act.view(-1).cpu().numpy() == la).all()
         want = torch.stack([pool[int(i)][int(j)] for i, j in zip(ix, iy)])
         assert torch.equal(h, want)
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=amp == "torch_amp"):
-            pool[x] = orig(h, act)[3]
+        pool[x] = nxt
 
 
 def test_graph_replay_equals_eager_and_is_repeatable():
@@ -122,3 +138,57 @@ def test_compat_path_with_reference_style_model():
     MCTS(cfg).search(r2, model, hidden, use_graph=False)
     assert r1.get_distributions() == r2.get_distributions()
     np.testing.assert_allclose(r1.get_values(), r2.get_values(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("small", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_recurrent_plan_matches_module(small, dtype):
+    """The folded/fused plan computes the same function as the nn.Module in eval mode (float
+    tolerance: BN folding and fp16 storage reorder roundings; stated here, not bit-exact)."""
+    from hanabizero_b200.model import MuZeroNet, MuZeroNetFull
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    a, inp = (11, 193) if small else (20, 785)
+    net = (MuZeroNet if small else MuZeroNetFull)(inp, a).randomize_heads(std=0.05).to(dev)
+    for m in net.modules():      # non-trivial BN statistics
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+    net.eval()
+    n = 257
+    hidden = torch.rand(n, 512, device=dev)
+    act = torch.randint(0, a, (n, 1), device=dev)
+    with torch.no_grad():
+        v0, r0, l0, s0 = net.recurrent_inference_device(hidden, act)
+    plan = net.recurrent_plan(dtype)
+    out_state = torch.empty(n, 512, device=dev, dtype=dtype)
+    v1, r1, l1 = plan.run(hidden.to(dtype), act, out_state)
+    tol = dict(rtol=2e-4, atol=2e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    torch.testing.assert_close(out_state.float(), s0, **tol)
+    torch.testing.assert_close(l1, l0, **tol)
+    torch.testing.assert_close(v1, v0, **tol)
+    torch.testing.assert_close(r1, r0, **tol)
+    # weight update -> refresh() re-folds in place (same buffers: captured graphs stay valid)
+    ptr_before = plan._w["W1"].data_ptr()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.01)
+    assert plan.refresh() and plan._w["W1"].data_ptr() == ptr_before and not plan.refresh()
+    with torch.no_grad():
+        v2, r2, l2, s2 = net.recurrent_inference_device(hidden, act)
+    v3, r3, l3 = plan.run(hidden.to(dtype), act, out_state)
+    torch.testing.assert_close(l3, l2, **tol)
+
+
+def test_plan_and_module_paths_select_the_same_actions():
+    from hanabizero_b200 import cytree
+    from hanabizero_b200.mcts import MCTS
+    dev, model, logits, hidden, legal, noise, cfg, a = _setup()
+    outs = []
+    for use_plan in (True, False):
+        roots = cytree.Roots(N, a, S)
+        roots.prepare(0.25, noise, [0.0] * N, logits, legal)
+        MCTS(cfg, use_plan=use_plan).run_multi(roots, model, hidden, use_graph=False)
+        outs.append(roots.get_stats_tensors())
+    agree = (outs[0][0].argmax(1) == outs[1][0].argmax(1)).float().mean().item()
+    assert agree > 0.9    # same function up to float rounding of the network; the trees see ~1e-6 different inputs
