@@ -40,6 +40,11 @@ SIGNATURES = {
     "hz_trees_backprop": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp]),
     "hz_trees_backprop_traverse": (_i, [_vp, _vp, _i, _f, _vp, _vp, _vp, _i, _vp, _f, _i, _f,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "hz_trees_search_step": (_i, [_vp, _vp, _i, _i, _vp]),
+    "hz_gemm_plan_create": (_i, [C.POINTER(_vp), _i, _i, _vp, _i]),
+    "hz_gemm_plan_destroy": (_i, [_vp]),
+    "hz_gemm_plan_steps": (_i, [_vp]),
+    "hz_gemm_plan_run": (_i, [_vp, _vp, _i, _i]),
     "hz_trees_set_progress": (_i, [_vp, _i]),
     "hz_trees_root_stats": (_i, [_vp, _vp, _vp, _vp]),
     "hz_trees_trajectories": (_i, [_vp, _vp, _vp, _i]),
@@ -58,6 +63,27 @@ SIGNATURES = {
     "hz_envs_dump": (_i, [_vp, _vp, _vp]),
 }
 
+
+
+class SearchIO(C.Structure):
+    """struct hz_search_io (include/hzb200.h)."""
+    _fields_ = [("value_logits", _vp), ("ld_value", _i64), ("reward_logits", _vp), ("ld_reward", _i64),
+                ("policy_logits", _vp), ("ld_policy", _i64), ("next_state", _vp), ("ld_state", _i64),
+                ("support", _vp), ("support_width", C.c_int32), ("support_delta", _f), ("elem_bytes", C.c_int32),
+                ("sanitize_nan", C.c_int32), ("pool", _vp), ("state_cols", C.c_int32), ("out_batch", _vp),
+                ("ld_batch", _i64), ("onehot_cols", C.c_int32), ("out_ix", _vp), ("out_action", _vp),
+                ("minmax", _vp), ("value_delta_max", _f), ("discount", _f), ("pb_c_base", C.c_int32),
+                ("pb_c_init", _f)]
+
+
+class GemmStep(C.Structure):
+    """struct hz_gemm_step (include/hzb200.h)."""
+    _fields_ = [("a", _vp), ("lda", _i64), ("stride_a", _i64), ("w", _vp), ("ldw", _i64), ("stride_w", _i64),
+                ("bias", _vp), ("stride_bias", _i64), ("c", _vp), ("ldc", _i64), ("stride_c", _i64),
+                ("d", _vp), ("ldd", _i64), ("stride_d", _i64), ("m", C.c_int32), ("n", C.c_int32),
+                ("k", C.c_int32), ("batch", C.c_int32), ("relu", C.c_int32)]
+
+
 _lib = None
 
 
@@ -70,6 +96,7 @@ def load():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -m hanabizero_b200.build` "
             "(nvcc, sm_100a). hanabizero_b200 has no CPU fallback.")
+    import torch  # noqa: F401  (brings libcublasLt.so.12 and the CUDA runtime libraries into the process)
     lib = C.CDLL(LIB_PATH)
     missing = [name for name in SIGNATURES if not hasattr(lib, name)]
     if missing:

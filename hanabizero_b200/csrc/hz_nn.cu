@@ -4,18 +4,9 @@
 //                      inverse scalar transform, NaN -> 0  (/root/reference/core/config.py:210-232,
 //                      which the reference runs as ~10 torch kernels and then copies to the host)
 //   hz_bias_act        GEMM epilogue: out = relu?(x + bias + residual + table[idx[row]])
-#include <cuda_fp16.h>
-
-#include "hz_common.cuh"
+#include "hz_decode.cuh"
 
 namespace hz {
-
-template <typename T> __device__ __forceinline__ float to_f(T v);
-template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
-template <typename T> __device__ __forceinline__ T from_f(float v);
-template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
-template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 // one warp per row of logits[rows][width]
 template <typename T>
@@ -26,30 +17,8 @@ __global__ void __launch_bounds__(128) k_support_decode(const T* __restrict__ lo
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const T* x = logits + (size_t)row * ld;
-  float m = -INFINITY;
-  for (int i = lane; i < width; i += 32) m = fmaxf(m, to_f(x[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(HZ_FULL, m, o));
-  float se = 0.0f, sw = 0.0f;
-  for (int i = lane; i < width; i += 32) {
-    const float e = expf(to_f(x[i]) - m);
-    se += e;
-    sw += e * support[i];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    se += __shfl_xor_sync(HZ_FULL, se, o);
-    sw += __shfl_xor_sync(HZ_FULL, sw, o);
-  }
-  if (lane == 0) {
-    const float eps = 0.001f;
-    const float v = (sw / se) / delta;
-    float r = (sqrtf(1.0f + 4.0f * eps * (fabsf(v) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
-    r = r * r - 1.0f;
-    r = (v < 0.0f ? -r : r) * delta;
-    out[row] = (r != r) ? 0.0f : r;
-  }
+  const float r = warp_support_decode<T>(logits + (size_t)row * ld, support, width, delta, lane);
+  if (lane == 0) out[row] = r;
 }
 
 // out[row][c] = act(x[row][c] + bias[c] + residual[row][c] + table[idx[row]][c]); V columns per thread

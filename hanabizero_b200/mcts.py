@@ -117,23 +117,50 @@ class MCTS(object):
             return
         check(lib.hz_trees_traverse(h, st, base, init, disc, mmp, delta, ptr(ws.ix), None, ptr(ws.la),
                                     ptr(ws.action64), ptr(ws.pool), ptr(ws.hidden), row_bytes))
-        plan = self._plan(model)
         for x in range(1, sims):
-            if plan is not None:   # next hidden state is written straight into its pool slot
-                value, reward, logits = plan.run(ws.hidden, ws.action64, ws.pool[x])
-            else:
-                with self._autocast():
-                    value, reward, logits, state = model.recurrent_inference_device(ws.hidden, ws.action64)
-                ws.pool[x].copy_(state)
-                value = value.float().contiguous()
-                reward = reward.float().contiguous()
-                logits = logits.float().contiguous()
+            with self._autocast():
+                value, reward, logits, state = model.recurrent_inference_device(ws.hidden, ws.action64)
+            ws.pool[x].copy_(state)
+            value = value.float().contiguous()
+            reward = reward.float().contiguous()
+            logits = logits.float().contiguous()
             if x < sims - 1:
                 check(lib.hz_trees_backprop_traverse(
                     h, st, x, disc, ptr(reward), ptr(value), ptr(logits), 1, mmp, delta, base, init,
                     ptr(ws.ix), None, ptr(ws.la), ptr(ws.action64), ptr(ws.pool), ptr(ws.hidden), row_bytes))
             else:
                 check(lib.hz_trees_backprop(h, st, x, disc, ptr(reward), ptr(value), ptr(logits), 1, mmp))
+
+    def _simulate_chain(self, roots, plan, ws):
+        """Device-resident loop on the fused plan: per simulation one GEMM chain (7 or 5 cuBLASLt
+        launches) and ONE tree launch that decodes the raw value/reward logits, expands, back-propagates,
+        stores the new hidden state in the pool, traverses and writes the next [hidden ‖ one-hot] batch."""
+        cfg, lib, h = self.config, roots._lib, roots.handle
+        sims = int(cfg.num_simulations)
+        st = torch.cuda.current_stream(roots.device).cuda_stream
+        mm = ws.minmax
+        mm.set_delta(cfg.value_delta_max)
+        mm.clear()
+        if sims < 2:
+            return
+        ch = plan.chain(roots.root_num)
+        io = _lib.SearchIO()
+        io.value_logits, io.ld_value = ptr(ch.value_logits), ch.value_logits.stride(0)
+        io.reward_logits, io.ld_reward = ptr(ch.reward_logits), ch.reward_logits.stride(0)
+        io.policy_logits, io.ld_policy = ptr(ch.policy_logits), ch.policy_logits.stride(0)
+        io.next_state, io.ld_state = ptr(ch.state), ch.state.stride(0)
+        io.support, io.support_width, io.support_delta = ptr(plan.support), plan.n_support, plan.net.support_delta
+        io.elem_bytes, io.sanitize_nan = ch.x0.element_size(), 1
+        io.pool, io.state_cols = ptr(ws.pool), plan.F
+        io.out_batch, io.ld_batch, io.onehot_cols = ptr(ch.x0), ch.x0.stride(0), plan.OH
+        io.out_ix, io.out_action = ptr(ws.ix), ptr(ws.la)
+        io.minmax, io.value_delta_max = ptr(mm.tensor(roots.device)), float(cfg.value_delta_max)
+        io.discount, io.pb_c_base, io.pb_c_init = float(cfg.discount), int(cfg.pb_c_base), float(cfg.pb_c_init)
+        ref = _lib.C.byref(io)
+        check(lib.hz_trees_search_step(h, st, 0, 1, ref))
+        for x in range(1, sims):
+            ch.run(st)
+            check(lib.hz_trees_search_step(h, st, x, 1 if x < sims - 1 else 0, ref))
 
     def _simulate_compat(self, roots, model, ws):
         """Same kernels around a model that only speaks the reference's NetworkOutput contract."""
@@ -164,18 +191,23 @@ class MCTS(object):
                 self._plan(model).refresh()   # re-fold weights in place if the module was updated
             ws.pool[0].copy_(cytree.as_device(hidden_state_roots, ws.pool.dtype, roots.device))
             sims = int(self.config.num_simulations)
-            if not hasattr(model, "recurrent_inference_device"):
+            plan = self._plan(model)
+            if plan is not None:
+                simulate = lambda: self._simulate_chain(roots, plan, ws)
+            else:
+                simulate = lambda: self._simulate(roots, model, ws)
+            if plan is None and not hasattr(model, "recurrent_inference_device"):
                 self._simulate_compat(roots, model, ws)
             elif not use_graph:
-                self._simulate(roots, model, ws)
+                simulate()
             elif ws.graph is None and ws.searches == 0:
-                self._simulate(roots, model, ws)  # first search runs eagerly (also warms cuBLAS)
+                simulate()  # first search runs eagerly (also warms cuBLAS)
             else:
                 if ws.graph is None:
                     torch.cuda.synchronize(roots.device)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
-                        self._simulate(roots, model, ws)
+                        simulate()
                     ws.graph = graph
                 ws.graph.replay()
                 # host-side progress of the handle is not touched by a replay

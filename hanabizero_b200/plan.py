@@ -1,25 +1,27 @@
 """Execution plan for `recurrent_inference` in eval mode: the same function as
-HanabiMuZeroNet.recurrent_inference_device (dynamics + reward/value/policy heads + inverse
-categorical transforms; /root/reference/core/model.py:74-84, config/hanabi_control/model.py), laid
-out for a latency-bound batch so one simulation costs ~16 launches instead of ~70:
+HanabiMuZeroNet.recurrent_inference_device (dynamics + reward/value/policy heads;
+/root/reference/core/model.py:74-84, config/hanabi_control/model.py:199-216, 301-318), laid out for
+a latency-bound batch.  A simulation is bounded by launch count, not FLOPs:
+PyTorch's module needs ~70 kernels per call; this plan needs 7 (Hanabi-Full) / 5 (Hanabi-Small)
+cuBLASLt GEMMs with fused epilogues (hz_gemm_plan, include/hzb200.h) and nothing else:
 
-  * BatchNorm (running statistics) folded into the preceding Linear;
-  * the one-hot action concat of `dynamics` (model.py:199-203, 301-305) replaced by a row lookup
-    E[a] = W_fc1[:, F + a] + b added in the GEMM epilogue;
-  * the first layer of the three heads run as one GEMM over the shared input;
-  * bias + ReLU fused into the cuBLASLt epilogue (torch._addmm_activation) or, where a residual or
-    the action row is involved, into one hz_bias_act launch; the next hidden state is written
-    straight into its slot of the search's hidden-state pool;
-  * value and reward decoded by one hz_support_decode launch.
+  * eval-mode BatchNorm folded into the preceding Linear;
+  * the one-hot action concat of `dynamics` is literal: the batch handed over by the tree kernel is
+    [hidden ‖ one-hot(action) ‖ 0-pad], so fc1 is one GEMM with K = 512 + 32;
+  * bias, ReLU and the residual adds run in the GEMM epilogues (beta = 1 with C = the skip input);
+  * the first layers of the three heads are one GEMM (shared input), their second layers one
+    strided-batched GEMM, the three output layers one strided-batched GEMM (policy rows zero-padded);
+  * value / reward logits are consumed raw by the tree kernel (hz_trees_search_step decodes them).
 
-The GEMMs are still torch/cuBLAS ("the network stays in PyTorch").  Folded weights live in fixed
-buffers that `refresh()` rewrites in place whenever the module's parameters change, so CUDA graphs
-captured over a plan stay valid across training updates.
+Weights live in fixed buffers that `refresh()` rewrites in place whenever the module's parameters
+change, so chains and CUDA graphs built over a plan stay valid across training updates.
 """
+import ctypes as C
+
 import torch
 
 from . import _lib
-from ._lib import check, ptr
+from ._lib import GemmStep, check, ptr
 
 
 def _fold(linear, bn):
@@ -31,13 +33,94 @@ def _fold(linear, bn):
     return w * scale[:, None], (b - bn.running_mean.detach().float()) * scale + bn.bias.detach().float()
 
 
-def _pad_rows(w, b, mult=8):
-    out = w.shape[0]
-    pad = (-out) % mult
-    if pad:
+def _pad_rows(w, b, rows):
+    pad = rows - w.shape[0]
+    if pad > 0:
         w = torch.cat((w, w.new_zeros(pad, w.shape[1])))
         b = torch.cat((b, b.new_zeros(pad)))
     return w, b
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class BoundChain:
+    """The plan instantiated for a fixed batch size: static activation buffers + the cuBLASLt chain."""
+
+    def __init__(self, plan, n):
+        self.plan, self.n = plan, n
+        dev, dt = plan.device, plan.dtype
+        F, H, KP, P3 = plan.F, plan.H, plan.KP, plan.P3
+        z = lambda *shape: torch.zeros(*shape, dtype=dt, device=dev)
+        self.x0 = z(n, KP)            # [hidden ‖ one-hot(action) ‖ 0]  <- written by the tree kernel
+        self.y1, self.y2 = z(n, F), z(n, F)
+        self.state = z(n, F)          # next hidden state (copied into the pool by the tree kernel)
+        self.h1 = z(n, 3 * H)
+        self.xb = z(4, n, H) if plan.full else None   # [a1, v2, r2, a2]
+        self.out = z(3, n, P3)        # value logits | reward logits | policy logits (first A columns)
+        w = plan._w
+        steps = []
+
+        def step(a, wt, bias, d, m, nn, k, c=None, relu=True, batch=1, sa=0, sw=0, sb=0, sc=0, sd=0, lda=None,
+                 ldc=None):
+            s = GemmStep()
+            s.a, s.lda, s.stride_a = a.data_ptr(), (a.stride(-2) if lda is None else lda), sa
+            s.w, s.ldw, s.stride_w = wt.data_ptr(), wt.stride(-2), sw
+            s.bias, s.stride_bias = bias.data_ptr(), sb
+            s.c, s.ldc, s.stride_c = (0 if c is None else c.data_ptr()), (0 if c is None else (c.stride(-2) if ldc is None else ldc)), sc
+            s.d, s.ldd, s.stride_d = d.data_ptr(), d.stride(-2), sd
+            s.m, s.n, s.k, s.batch, s.relu = m, nn, k, batch, 1 if relu else 0
+            steps.append(s)
+
+        if plan.full:
+            # dynamics: relu(bn1 fc1 [s‖a]) -> relu(bn2 fc2) -> relu(bn3 fc3 + s)
+            step(self.x0, w["W1"], w["b1"], self.y1, n, F, KP)
+            step(self.y1, w["W2"], w["b2"], self.y2, n, F, F)
+            step(self.y2, w["W3"], w["b3"], self.state, n, F, F, c=self.x0)
+            # heads: [actor | value | reward] first layers, then [a1 | v2 | r2], a2 (+skip), outputs
+            step(self.state, w["Wh1"], w["bh1"], self.h1, n, 3 * H, F)
+            step(self.h1, w["WB2"], w["bB2"], self.xb, n, H, H, batch=3, sa=H, sw=H * H, sb=H, sd=n * H,
+                 lda=3 * H)
+            step(self.xb[0], w["Wa2"], w["ba2"], self.xb[3], n, H, H, c=self.h1)
+            step(self.xb[1], w["WB3"], w["bB3"], self.out, n, P3, H, relu=False, batch=3, sa=n * H, sw=P3 * H,
+                 sb=P3, sd=n * P3)
+        else:
+            # dynamics: relu(bn1 fc1 [s‖a] + s) -> relu(bn2 fc2) -> relu(bn3 fc3)
+            step(self.x0, w["W1"], w["b1"], self.y1, n, F, KP, c=self.x0)
+            step(self.y1, w["W2"], w["b2"], self.y2, n, F, F)
+            step(self.y2, w["W3"], w["b3"], self.state, n, F, F)
+            step(self.state, w["Wh1"], w["bh1"], self.h1, n, 3 * H, F)   # [value | reward | actor]
+            step(self.h1, w["WB3"], w["bB3"], self.out, n, P3, H, relu=False, batch=3, sa=H, sw=P3 * H, sb=P3,
+                 sd=n * P3, lda=3 * H)
+        self.n_steps = len(steps)
+        arr = (GemmStep * self.n_steps)(*steps)
+        self._h = C.c_void_p()
+        check(plan.lib.hz_gemm_plan_create(C.byref(self._h), dev.index, self.x0.element_size(), arr, self.n_steps))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self.plan.lib.hz_gemm_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def run(self, stream):
+        check(self.plan.lib.hz_gemm_plan_run(self._h, stream, 0, self.n_steps))
+
+    @property
+    def value_logits(self):
+        return self.out[0]
+
+    @property
+    def reward_logits(self):
+        return self.out[1]
+
+    @property
+    def policy_logits(self):
+        return self.out[2]
 
 
 class RecurrentPlan:
@@ -45,15 +128,19 @@ class RecurrentPlan:
         if dtype not in (torch.float16, torch.float32):
             raise ValueError("plan dtype must be float16 or float32")
         self.net, self.dtype = net, dtype
+        self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("RecurrentPlan needs the module on a CUDA device (no CPU fallback)")
         self.lib = _lib.load()
-        self.F = net.feature_size
-        self.A = net.action_space_n
-        self.H = net.hidden_size
-        self.full = net.full
-        self.n_value = net._value_support.numel()
-        self.n_reward = net._reward_support.numel()
-        self._sig = None
-        self._w = {}
+        self.F, self.A, self.H, self.full = net.feature_size, net.action_space_n, net.hidden_size, net.full
+        self.OH = _round_up(self.A, 16)            # one-hot columns handed over by the tree kernel
+        self.KP = self.F + self.OH
+        self.n_support = net._value_support.numel()
+        if net._reward_support.numel() != self.n_support:
+            raise ValueError("value and reward supports must have the same size")
+        self.P3 = _round_up(self.n_support, 8)
+        self.support = net._value_support.detach().float().contiguous()
+        self._sig, self._w, self._chains = None, {}, {}
         self.refresh(force=True)
 
     # -- weights ---------------------------------------------------------------------------------------
@@ -74,83 +161,61 @@ class RecurrentPlan:
         sig = self._signature()
         if not force and sig == self._sig:
             return False
-        net, F = self.net, self.F
+        net, F, A = self.net, self.F, self.A
         d = net._dynamics_state
         w1, b1 = _fold(d.fc1, d.bn1)
-        self._set("W1", w1[:, :F])                           # [F, F] state part
-        self._set("E1", w1[:, F:].t() + b1[None, :])         # [A, F] action row + bias
+        w1c = w1.new_zeros(F, self.KP)
+        w1c[:, :F + A] = w1
+        self._set("W1", w1c)
+        self._set("b1", b1)
         for i, (fc, bn) in ((2, (d.fc2, d.bn2)), (3, (d.fc3, d.bn3))):
             w, b = _fold(fc, bn)
             self._set(f"W{i}", w)
             self._set(f"b{i}", b)
         v, r, p = net._prediction_value, net._dynamics_reward, net._prediction_actor
-        heads1 = [_fold(h[0], h[1]) for h in (v, r, p)]
-        self._set("Wh1", torch.cat([w for w, _ in heads1]))  # [3H, F]: value | reward | actor
+        fv, fr, fp = (v[6], r[6], p[4]) if self.full else (v[3], r[3], p[3])
+        order = (p, v, r) if self.full else (v, r, p)
+        heads1 = [_fold(h[0], h[1]) for h in order]
+        self._set("Wh1", torch.cat([w for w, _ in heads1]))
         self._set("bh1", torch.cat([b for _, b in heads1]))
         if self.full:
-            for name, (fc, bn) in (("v2", (v[3], v[4])), ("r2", (r[3], r[4])), ("a1", (p[3].fc1, p[3].bn1)),
-                                   ("a2", (p[3].fc2, p[3].bn2))):
-                w, b = _fold(fc, bn)
-                self._set("W" + name, w)
-                self._set("b" + name, b)
-            finals = (("v", v[6]), ("r", r[6]), ("p", p[4]))
-        else:
-            finals = (("v", v[3]), ("r", r[3]), ("p", p[3]))
-        for name, fc in finals:
-            w, b = _pad_rows(*_fold(fc, None))
-            self._set("Wf" + name, w)
-            self._set("bf" + name, b)
+            second = [_fold(p[3].fc1, p[3].bn1), _fold(v[3], v[4]), _fold(r[3], r[4])]   # a1 | v2 | r2
+            self._set("WB2", torch.stack([w for w, _ in second]))
+            self._set("bB2", torch.stack([b for _, b in second]))
+            wa2, ba2 = _fold(p[3].fc2, p[3].bn2)
+            self._set("Wa2", wa2)
+            self._set("ba2", ba2)
+        outs = [_pad_rows(*_fold(fc, None), self.P3) for fc in (fv, fr, fp)]                # value | reward | policy
+        self._set("WB3", torch.stack([w for w, _ in outs]))
+        self._set("bB3", torch.stack([b for _, b in outs]))
         self._sig = sig
         return True
 
     # -- execution -------------------------------------------------------------------------------------
-    def _epi(self, st, out, x, bias=None, residual=None, table=None, idx=None, relu=True):
-        check(self.lib.hz_bias_act(st, ptr(out), out.stride(0), ptr(x), x.stride(0), ptr(bias), ptr(residual),
-                                   0 if residual is None else residual.stride(0), ptr(table), ptr(idx),
-                                   x.shape[0], x.shape[1], 1 if relu else 0, x.element_size()))
-        return out
+    def chain(self, n):
+        """Static buffers + GEMM chain for batch size n (cached)."""
+        c = self._chains.get(n)
+        if c is None:
+            if len(self._chains) >= 4:
+                self._chains.pop(next(iter(self._chains)))
+            c = self._chains[n] = BoundChain(self, n)
+        return c
 
     @torch.no_grad()
     def run(self, hidden, action, out_state):
-        """hidden [N, F] (plan dtype), action int64 [N] or [N, 1], out_state [N, F] (plan dtype, may be
-        a slot of the hidden-state pool).  Returns (value [N], reward [N], policy_logits [N, A]) fp32."""
-        w, H, n = self._w, self.H, hidden.shape[0]
-        st = torch.cuda.current_stream(hidden.device).cuda_stream
-        act = action.reshape(-1)
-        addmm_act = torch._addmm_activation
-        # dynamics
-        y = torch.mm(hidden, w["W1"].t())
-        if self.full:   # relu(bn1(fc1 [s ‖ a]))  ...  relu(bn3(fc3 .) + s)
-            self._epi(st, y, y, table=w["E1"], idx=act)
-            y = addmm_act(w["b2"], y, w["W2"].t())
-            z = torch.mm(y, w["W3"].t())
-            self._epi(st, out_state, z, bias=w["b3"], residual=hidden)
-        else:           # relu(bn1(fc1 [s ‖ a]) + s)  ...  relu(bn3(fc3 .))
-            self._epi(st, y, y, residual=hidden, table=w["E1"], idx=act)
-            y = addmm_act(w["b2"], y, w["W2"].t())
-            z = torch.mm(y, w["W3"].t())
-            self._epi(st, out_state, z, bias=w["b3"])
-        # heads: first layers share their input
-        h1 = addmm_act(w["bh1"], out_state, w["Wh1"].t())       # [N, 3H] = value | reward | actor
-        hv, hr, ha = h1[:, :H], h1[:, H:2 * H], h1[:, 2 * H:]
-        if self.full:
-            hv = addmm_act(w["bv2"], hv, w["Wv2"].t())
-            hr = addmm_act(w["br2"], hr, w["Wr2"].t())
-            a1 = addmm_act(w["ba1"], ha, w["Wa1"].t())
-            a2 = torch.mm(a1, w["Wa2"].t())
-            ha = self._epi(st, a2, a2, bias=w["ba2"], residual=ha)
-        wide = w["Wfv"].shape[0]
-        vr = torch.empty(2 * n, wide, dtype=self.dtype, device=hidden.device)
-        torch.addmm(w["bfv"], hv, w["Wfv"].t(), out=vr[:n])
-        torch.addmm(w["bfr"], hr, w["Wfr"].t(), out=vr[n:])
-        logits = torch.addmm(w["bfp"], ha, w["Wfp"].t())[:, :self.A].float().contiguous()
-        out = torch.empty(2 * n, dtype=torch.float32, device=hidden.device)
-        if self.n_value == self.n_reward:
-            check(self.lib.hz_support_decode(st, ptr(vr), vr.element_size(), ptr(self.net._value_support), ptr(out),
-                                             2 * n, self.n_value, vr.stride(0), self.net.support_delta))
-        else:
-            check(self.lib.hz_support_decode(st, ptr(vr), vr.element_size(), ptr(self.net._value_support), ptr(out),
-                                             n, self.n_value, vr.stride(0), self.net.support_delta))
-            check(self.lib.hz_support_decode(st, ptr(vr[n:]), vr.element_size(), ptr(self.net._reward_support),
-                                             ptr(out[n:]), n, self.n_reward, vr.stride(0), self.net.support_delta))
-        return out[:n], out[n:], logits
+        """Standalone call with the module's signature: hidden [N, F], action int64 [N] or [N, 1],
+        out_state [N, F] (plan dtype).  Returns (value [N], reward [N], policy_logits [N, A]) fp32.
+        (The search loop does not use this: the tree kernel writes/reads the chain's buffers directly.)"""
+        n = hidden.shape[0]
+        ch = self.chain(n)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        ch.x0[:, :self.F].copy_(hidden)
+        ch.x0[:, self.F:].zero_()
+        ch.x0[:, self.F:].scatter_(1, action.reshape(-1, 1), 1.0)
+        ch.run(st)
+        out_state.copy_(ch.state)
+        dec = torch.empty(2 * n, dtype=torch.float32, device=self.device)
+        vr = ch.out[:2].reshape(2 * n, self.P3)
+        check(self.lib.hz_support_decode(st, ptr(vr), vr.element_size(), ptr(self.support), ptr(dec), 2 * n,
+                                         self.n_support, self.P3, self.net.support_delta))
+        return dec[:n], dec[n:], ch.policy_logits[:, :self.A].float().contiguous()

@@ -91,6 +91,41 @@ int hz_trees_backprop_traverse(hz_trees* t, void* stream, int hidden_state_index
                                int32_t* out_action, int64_t* out_action64, const void* pool,
                                void* out_hidden, int row_bytes);
 
+/* One launch per simulation for the device-resident loop, consuming the network's RAW outputs:
+ *   x == 0 : traverse only (first simulation after prepare);
+ *   x >= 1 : decode value/reward of simulation x from their categorical logits
+ *            (core/config.py:210-232), expand + back-propagate (as hz_trees_backprop), store the new
+ *            node's hidden state into pool[x], then (do_traverse != 0) traverse for simulation
+ *            x+1 and write the next network input batch: the parent's hidden state followed by
+ *            one-hot(last action) (the concat of dynamics(), config/hanabi_control/model.py:199-203). */
+typedef struct hz_search_io {
+  /* network outputs of simulation x, row-major, `elem_bytes` per element (2 = half, 4 = float) */
+  const void* value_logits;   int64_t ld_value;    /* [N][support_width] */
+  const void* reward_logits;  int64_t ld_reward;   /* [N][support_width] */
+  const void* policy_logits;  int64_t ld_policy;   /* [N][A] */
+  const void* next_state;     int64_t ld_state;    /* [N][state_cols] */
+  const float* support;       /* dev float[support_width] */
+  int32_t support_width;
+  float support_delta;
+  int32_t elem_bytes;
+  int32_t sanitize_nan;       /* zero NaN policy logits (core/mcts.py:48-49) */
+  /* hidden-state pool and the batch handed to the network */
+  void* pool;                 /* [capacity+1][N][state_cols], elem_bytes each */
+  int32_t state_cols;         /* state_cols * elem_bytes must be a multiple of 16 */
+  void* out_batch;            /* [N][ld_batch]: state_cols of hidden state, then onehot_cols of one-hot */
+  int64_t ld_batch;           /* elements; ld_batch * elem_bytes multiple of 16 */
+  int32_t onehot_cols;        /* 0..32; columns >= num_actions stay zero */
+  int32_t* out_ix;            /* optional int32[N]: parent hidden-state index x */
+  int32_t* out_action;        /* optional int32[N]: last action */
+  /* search constants */
+  float* minmax;              /* dev float[N][2], read and written */
+  float value_delta_max;
+  float discount;
+  int32_t pb_c_base;
+  float pb_c_init;
+} hz_search_io;
+int hz_trees_search_step(hz_trees* t, void* stream, int x, int do_traverse, const hz_search_io* io);
+
 /* After replaying a CUDA graph that contains the calls above, the handle's host-side progress
  * (number of completed back-propagations since prepare) must be restored by hand: a replay runs
  * the kernels but not the host code.  expansions in [0, capacity]. */
@@ -177,6 +212,23 @@ int hz_support_decode(void* stream, const void* logits, int elem_bytes, const fl
 int hz_bias_act(void* stream, void* out, int64_t ld_out, const void* x, int64_t ld_x, const void* bias,
                 const void* residual, int64_t ld_res, const void* table, const int64_t* idx,
                 int rows, int cols, int relu, int elem_bytes);
+
+/* A fixed chain of nn.Linear-shaped GEMMs executed with cuBLASLt, one launch each:
+ *   D[m][n] = act( A[m][k] . W[n][k]^T + bias[n] + C[m][n] ),  all row-major, strided batches allowed.
+ * Pointers are captured at creation (static buffers: the chain is CUDA-graph friendly). */
+typedef struct hz_gemm_step {
+  const void* a;    int64_t lda; int64_t stride_a;     /* activations */
+  const void* w;    int64_t ldw; int64_t stride_w;     /* weights in nn.Linear layout [n][k] */
+  const void* bias; int64_t stride_bias;               /* [n] or NULL */
+  const void* c;    int64_t ldc; int64_t stride_c;     /* residual or NULL */
+  void* d;          int64_t ldd; int64_t stride_d;     /* output */
+  int32_t m, n, k, batch, relu;
+} hz_gemm_step;
+typedef struct hz_gemm_plan hz_gemm_plan;
+int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz_gemm_step* steps, int n_steps); /* sync */
+int hz_gemm_plan_destroy(hz_gemm_plan* p);                                                                     /* sync */
+int hz_gemm_plan_steps(const hz_gemm_plan* p);
+int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count);
 
 #ifdef __cplusplus
 }

@@ -25,20 +25,25 @@ def _setup(amp="none", small=False):
     return dev, model, logits, hidden, legal, noise, SearchConfig(num_simulations=S, amp_type=amp), a
 
 
-def _record(model, plan=None):
-    """Record (value, reward, logits, hidden_in, action_in, next_state) of every network call made by
-    the search, on the nn.Module path or on the fused-plan path."""
+class PlanAsModel:
+    """Runs the fused plan through the generic device-resident path (plan.run + hz_trees_backprop_traverse),
+    so that its network outputs can be recorded and replayed through the oracle."""
+
+    def __init__(self, plan):
+        self.plan = plan
+
+    def eval(self):
+        return self
+
+    def recurrent_inference_device(self, h, act):
+        state = torch.empty_like(h)
+        v, r, lg = self.plan.run(h, act, state)
+        return v, r, lg, state
+
+
+def _record(model):
+    """Record (value, reward, logits, hidden_in, action_in, next_state) of every network call of the search."""
     rec = []
-    if plan is not None:
-        orig = plan.run
-
-        def wrapped_plan(h, act, out_state):
-            v, r, lg = orig(h, act, out_state)
-            rec.append((v.clone(), r.clone(), lg.clone(), h.detach().clone(), act.detach().clone(), out_state.clone()))
-            return v, r, lg
-
-        plan.run = wrapped_plan
-        return rec, orig
     orig = model.recurrent_inference_device
 
     def wrapped(h, act):
@@ -69,15 +74,13 @@ def test_run_multi_matches_oracle_given_same_network_outputs(amp, small, use_pla
     from hanabizero_b200 import cytree
     from hanabizero_b200.mcts import MCTS
     dev, model, logits, hidden, legal, noise, cfg, a = _setup(amp, small)
-    plan = model.recurrent_plan(torch.float16 if amp == "torch_amp" else torch.float32) if use_plan else None
-    rec, orig = _record(model, plan)
+    dtype = torch.float16 if amp == "torch_amp" else torch.float32
+    net = PlanAsModel(model.recurrent_plan(dtype)) if use_plan else model
+    rec, orig = _record(net)
     roots = cytree.Roots(N, a, S)
     roots.prepare(0.25, noise, [0.0] * N, logits, legal)
-    MCTS(cfg, use_plan=use_plan).run_multi(roots, model, hidden, use_graph=False)
-    if use_plan:
-        plan.run = orig
-    else:
-        model.recurrent_inference_device = orig
+    MCTS(cfg, use_plan=False).run_multi(roots, net, hidden.to(dtype) if use_plan else hidden, use_graph=False)
+    net.recurrent_inference_device = orig
     assert len(rec) == S - 1                               # the last iteration is skipped (core/mcts.py:25-26)
     cpu, trace = _oracle_replay(rec, cfg, noise, logits, legal, a)
     visits, values = roots.get_stats_tensors()
@@ -85,12 +88,37 @@ def test_run_multi_matches_oracle_given_same_network_outputs(amp, small, use_pla
     assert (visits.cpu().numpy() == ov).all()
     np.testing.assert_allclose(values.cpu().numpy(), oval, rtol=1e-5)
     # the batches handed to the network are the parents' hidden states and the last actions
-    pool = [hidden.to(rec[0][3].dtype)] + [None] * S
+    pool = [(hidden.to(dtype) if use_plan else hidden).to(rec[0][3].dtype)] + [None] * S
     for x, ((v, rw, lg, h, act, nxt), (ix, iy, la)) in enumerate(zip(rec, trace), start=1):
         assert (act.view(-1).cpu().numpy() == la).all()
         want = torch.stack([pool[int(i)][int(j)] for i, j in zip(ix, iy)])
         assert torch.equal(h, want)
         pool[x] = nxt
+
+
+@pytest.mark.parametrize("amp,small", [("none", False), ("torch_amp", False), ("none", True), ("torch_amp", True)])
+def test_fused_search_step_path_equals_generic_path(amp, small):
+    """The production path (GEMM chain + hz_trees_search_step decoding raw logits in the tree kernel)
+    must give bit-identical trees to the generic path around the same plan, which the test above
+    ties to the oracle."""
+    from hanabizero_b200 import cytree
+    from hanabizero_b200.mcts import MCTS
+    dev, model, logits, hidden, legal, noise, cfg, a = _setup(amp, small)
+    dtype = torch.float16 if amp == "torch_amp" else torch.float32
+    outs = []
+    for fused in (True, False):
+        roots = cytree.Roots(N, a, S)
+        roots.prepare(0.25, noise, [0.0] * N, logits, legal)
+        if fused:
+            MCTS(cfg, use_plan=True).run_multi(roots, model, hidden, use_graph=False)
+        else:
+            MCTS(cfg, use_plan=False).run_multi(roots, PlanAsModel(model.recurrent_plan(dtype)), hidden.to(dtype), use_graph=False)
+        v, val = roots.get_stats_tensors()
+        e = roots.export(S)
+        outs.append((v.cpu(), val.cpu(), e["visits"].cpu(), e["value_sum"].cpu(), e["reward"].cpu()))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+    assert (outs[0][0].sum(1) == S - 1).all()
 
 
 def test_graph_replay_equals_eager_and_is_repeatable():
@@ -135,7 +163,7 @@ def test_compat_path_with_reference_style_model():
     for r in (r1, r2):
         r.prepare(0.25, noise, [0.0] * N, logits, legal)
     MCTS(cfg).run_multi(r1, RefStyle(model), hidden.cpu().numpy())
-    MCTS(cfg).search(r2, model, hidden, use_graph=False)
+    MCTS(cfg, use_plan=False).search(r2, model, hidden, use_graph=False)
     assert r1.get_distributions() == r2.get_distributions()
     np.testing.assert_allclose(r1.get_values(), r2.get_values(), rtol=1e-5)
 
