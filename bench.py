@@ -398,39 +398,73 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # the production launch: hz_trees_search_step (decode + expand + backprop + min/max + traverse +
+        # hand-off) on synthetic network outputs, alone on the stream, L2 flushed before every launch
+        plan = model.recurrent_plan(torch.float16 if args.amp == "torch_amp" else torch.float32)
+        ch = plan.chain(N)
+        eb = ch.x0.element_size()
+        ch.out.copy_(torch.randn_like(ch.out.float()).to(ch.out.dtype))
+        ch.state.copy_(torch.rand_like(ch.state.float()).to(ch.state.dtype))
         roots = cytree.Roots(N, A, S, device=dev)
         roots.prepare(CONST["frac"], noise, zeros_r, root_logits, legal_i)
-        mm = cytree.MinMaxStatsList(N); mm.set_delta(CONST["delta"]); mmp = mm.tensor(dev).data_ptr()
-        pool = torch.randn(S, N, F, device=dev, dtype=root_hidden.dtype)
-        hidden = torch.empty(N, F, device=dev, dtype=root_hidden.dtype)
-        act64 = torch.empty(N, 1, dtype=torch.int64, device=dev)
-        sr = torch.randn(S, N, device=dev); sv = torch.randn(S, N, device=dev); sl = torch.randn(S, N, A, device=dev)
+        mm = cytree.MinMaxStatsList(N); mm.set_delta(CONST["delta"])
+        pool = torch.rand(S, N, F, device=dev).to(ch.x0.dtype)
+        io = _lib.SearchIO()
+        io.value_logits, io.ld_value = ch.value_logits.data_ptr(), ch.value_logits.stride(0)
+        io.reward_logits, io.ld_reward = ch.reward_logits.data_ptr(), ch.reward_logits.stride(0)
+        io.policy_logits, io.ld_policy = ch.policy_logits.data_ptr(), ch.policy_logits.stride(0)
+        io.next_state, io.ld_state = ch.state.data_ptr(), ch.state.stride(0)
+        io.support, io.support_width, io.support_delta = plan.support.data_ptr(), plan.n_support, plan.net.support_delta
+        io.elem_bytes, io.sanitize_nan = eb, 1
+        io.pool, io.state_cols = pool.data_ptr(), F
+        io.out_batch, io.ld_batch, io.onehot_cols = ch.x0.data_ptr(), ch.x0.stride(0), plan.OH
+        io.out_ix, io.out_action = None, None
+        io.minmax, io.value_delta_max = mm.tensor(dev).data_ptr(), CONST["delta"]
+        io.discount, io.pb_c_base, io.pb_c_init = CONST["discount"], CONST["pb_c_base"], CONST["pb_c_init"]
         st = torch.cuda.current_stream().cuda_stream
-        rb = F * hidden.element_size()
-        _lib.check(lib.hz_trees_traverse(roots.handle, st, CONST["pb_c_base"], CONST["pb_c_init"], CONST["discount"], mmp,
-                                         CONST["delta"], None, None, None, act64.data_ptr(), pool.data_ptr(), hidden.data_ptr(), rb))
+        ref = _lib.C.byref(io)
+        _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         depth_sum = 0.0
         for x in range(1, S - 1):
-            flush.fill_(x & 1)  # evict L2 between launches: each launch starts cold like inside a real search
+            flush.fill_(x & 1)  # evict L2: every launch starts cold, like inside a search whose working set exceeds L2
             evs[x][0].record()
-            _lib.check(lib.hz_trees_backprop_traverse(
-                roots.handle, st, x, CONST["discount"], sr[x].data_ptr(), sv[x].data_ptr(), sl[x].data_ptr(), 1, mmp,
-                CONST["delta"], CONST["pb_c_base"], CONST["pb_c_init"], None, None, None, act64.data_ptr(),
-                pool.data_ptr(), hidden.data_ptr(), rb))
+            _lib.check(lib.hz_trees_search_step(roots.handle, st, x, 1, ref))
             evs[x][1].record()
             depth_sum += float(roots.export(1)["path_len"].float().mean().item()) - 1.0
         torch.cuda.synchronize()
         durs = [evs[x][0].elapsed_time(evs[x][1]) * 1e-3 for x in range(1, S - 1)]
+        # the same launches back to back inside a CUDA graph, no flush (what the search loop sees: 270 MB of
+        # tree + pool per search is larger than L2, but the hot nodes of a tree stay L2-resident between sims)
+        roots.prepare(CONST["frac"], noise, zeros_r, root_logits, legal_i)
+        mm.clear()
+        _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            st_c = torch.cuda.current_stream().cuda_stream
+            for x in range(1, S - 1):
+                _lib.check(lib.hz_trees_search_step(roots.handle, st_c, x, 1, ref))
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        gr.replay()
+        w1.record()
+        torch.cuda.synchronize()
+        warm_us = w0.elapsed_time(w1) * 1e3 / (S - 2)
+        _lib.check(lib.hz_trees_set_progress(roots.handle, S - 2))
         n_l = len(durs)
         D = depth_sum / n_l
         s_mean = statistics.mean(range(1, S - 1))
-        bytes_launch = N * b_sim(A, D, s_mean, F * hidden.element_size() / 4.0)
+        # SURVEY §8d per-simulation bytes (tree part with the hidden row in the model dtype) + what this fused
+        # launch additionally replaces: reading both support-logit rows and copying the new state into the pool
+        per_tree = b_sim(A, D, s_mean, F * eb / 4.0) + 2 * plan.n_support * eb + 2 * F * eb
+        bytes_launch = N * per_tree
         achieved = bytes_launch / statistics.mean(durs) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_tree_step<backprop,traverse,gather>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "launch_us": 1e6 * statistics.mean(durs), "algorithmic_bytes_per_launch": bytes_launch,
+        roof = {"bound": "hbm", "kernel": "k_search_step<half,backprop,traverse> (hz_trees_search_step)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launch_us": 1e6 * statistics.mean(durs), "launch_us_in_graph_no_flush": warm_us,
+                "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_tree": per_tree,
                 "mean_depth": D, "l2": "flushed before every timed launch (256 MiB write)"}
         # env kernel
         evs2 = []

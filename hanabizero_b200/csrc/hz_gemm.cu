@@ -11,6 +11,8 @@
 // column-major: D^T[N,M] = W(col-major view [K,N], op T) · A^T(col-major view [K,M], op N).
 #include <cublasLt.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "hz_common.cuh"
@@ -44,6 +46,7 @@ struct hz_gemm_plan {
   cublasLtHandle_t lt = nullptr;
   void* workspace = nullptr;
   size_t ws_bytes = 0;
+  bool autotune = true;
   std::vector<LtStep> steps;
 };
 
@@ -100,15 +103,50 @@ static int build_step(hz_gemm_plan* p, LtStep& st) {
   HZ_LT(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_B_BYTES, &ab, sizeof(ab)));
   HZ_LT(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_C_BYTES, &ac, sizeof(ac)));
   HZ_LT(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MIN_ALIGNMENT_D_BYTES, &ad, sizeof(ad)));
-  cublasLtMatmulHeuristicResult_t res{};
+  constexpr int kCand = 12;
+  cublasLtMatmulHeuristicResult_t res[kCand];
   int found = 0;
-  cublasStatus_t hs = cublasLtMatmulAlgoGetHeuristic(p->lt, st.op, st.la, st.lb, st.lc, st.ld, pref, 1, &res, &found);
+  cublasStatus_t hs = cublasLtMatmulAlgoGetHeuristic(p->lt, st.op, st.la, st.lb, st.lc, st.ld, pref, kCand, res, &found);
   cublasLtMatmulPreferenceDestroy(pref);
   if (hs != CUBLAS_STATUS_SUCCESS || found == 0) {
     set_error("cuBLASLt has no algorithm for GEMM m=%d n=%d k=%d batch=%d (status %d)", s.m, s.n, s.k, s.batch, (int)hs);
     return HZ_ERR_CUDA;
   }
-  st.algo = res.algo;
+  st.algo = res[0].algo;
+  if (p->autotune && found > 1) {
+    // the chain is latency-bound and the shapes are fixed: time the heuristic's candidates once and keep
+    // the fastest (outputs are scratch at this point; every candidate computes the same D)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const float alpha = 1.0f;
+    float best = 1e30f;
+    for (int c = 0; c < found; ++c) {
+      if (res[c].state != CUBLAS_STATUS_SUCCESS || res[c].workspaceSize > p->ws_bytes) continue;
+      bool ok = true;
+      for (int rep = 0; rep < 3 && ok; ++rep) {
+        ok = cublasLtMatmul(p->lt, st.op, &alpha, s.w, st.la, s.a, st.lb, &st.beta, s.c ? s.c : s.d, st.lc, s.d, st.ld,
+                            &res[c].algo, p->workspace, p->ws_bytes, 0) == CUBLAS_STATUS_SUCCESS;
+      }
+      if (!ok) continue;
+      cudaEventRecord(e0, 0);
+      for (int rep = 0; rep < 20; ++rep) {
+        cublasLtMatmul(p->lt, st.op, &alpha, s.w, st.la, s.a, st.lb, &st.beta, s.c ? s.c : s.d, st.lc, s.d, st.ld,
+                       &res[c].algo, p->workspace, p->ws_bytes, 0);
+      }
+      cudaEventRecord(e1, 0);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { ok = false; }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (ok && ms < best) {
+        best = ms;
+        st.algo = res[c].algo;
+      }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaGetLastError();
+  }
   return HZ_OK;
 }
 
@@ -142,6 +180,10 @@ int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz
   p->device = device;
   p->elem_bytes = elem_bytes;
   p->ws_bytes = 32u << 20;
+  {
+    const char* env = getenv("HZ_GEMM_AUTOTUNE");
+    p->autotune = !(env && env[0] == '0');
+  }
   if (cublasLtCreate(&p->lt) != CUBLAS_STATUS_SUCCESS) { delete p; set_error("cublasLtCreate failed"); return HZ_ERR_CUDA; }
   cudaError_t e = cudaMalloc(&p->workspace, p->ws_bytes);
   if (e != cudaSuccess) { cublasLtDestroy(p->lt); delete p; return fail_cuda(e, "hz_gemm_plan_create: workspace"); }

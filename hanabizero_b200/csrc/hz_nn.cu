@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) k_support_decode(const T* __restrict__ lo
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float r = warp_support_decode<T>(logits + (size_t)row * ld, support, width, delta, lane);
+  const float r = warp_support_decode<T>(logits + (size_t)row * ld, support, width, delta, ld, lane);
   if (lane == 0) out[row] = r;
 }
 
@@ -95,7 +95,8 @@ extern "C" {
 
 int hz_support_decode(void* stream, const void* logits, int elem_bytes, const float* support,
                       float* out, int rows, int width, int64_t ld, float delta) {
-  if (!logits || !support || !out || rows <= 0 || width <= 0 || ld < width || (elem_bytes != 2 && elem_bytes != 4)) {
+  if (!logits || !support || !out || rows <= 0 || width <= 0 || width > 256 || ld < width ||
+      (elem_bytes != 2 && elem_bytes != 4)) {
     set_error("hz_support_decode: bad argument");
     return HZ_ERR_ARG;
   }
