@@ -426,13 +426,18 @@ def run_ours(args):
         _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        depth_sum = 0.0
+        depth_sum, depth_max = 0.0, []
+        gen_out = torch.Generator(device=dev).manual_seed(99)
+        outs = [torch.randn(ch.out.shape, device=dev, generator=gen_out).to(ch.out.dtype) for _ in range(8)]
         for x in range(1, S - 1):
+            ch.out.copy_(outs[x % 8])   # fresh synthetic network outputs per simulation (realistic tree depths)
             flush.fill_(x & 1)  # evict L2: every launch starts cold, like inside a search whose working set exceeds L2
             evs[x][0].record()
             _lib.check(lib.hz_trees_search_step(roots.handle, st, x, 1, ref))
             evs[x][1].record()
-            depth_sum += float(roots.export(1)["path_len"].float().mean().item()) - 1.0
+            pl = roots.export(1)["path_len"].float()
+            depth_sum += float(pl.mean().item()) - 1.0
+            depth_max.append(int(pl.max().item()) - 1)
         torch.cuda.synchronize()
         durs = [evs[x][0].elapsed_time(evs[x][1]) * 1e-3 for x in range(1, S - 1)]
         # the same launches back to back inside a CUDA graph, no flush (what the search loop sees: 270 MB of
@@ -445,14 +450,24 @@ def run_ours(args):
         with torch.cuda.graph(gr):
             st_c = torch.cuda.current_stream().cuda_stream
             for x in range(1, S - 1):
+                ch.out.copy_(outs[x % 8])
                 _lib.check(lib.hz_trees_search_step(roots.handle, st_c, x, 1, ref))
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0.record()
         gr.replay()
         w1.record()
         torch.cuda.synchronize()
-        warm_us = w0.elapsed_time(w1) * 1e3 / (S - 2)
         _lib.check(lib.hz_trees_set_progress(roots.handle, S - 2))
+        gc = torch.cuda.CUDAGraph()      # the same graph without the tree launches: the copies' own cost
+        with torch.cuda.graph(gc):
+            for x in range(1, S - 1):
+                ch.out.copy_(outs[x % 8])
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        gc.replay()
+        c1.record()
+        torch.cuda.synchronize()
+        warm_us = (w0.elapsed_time(w1) - c0.elapsed_time(c1)) * 1e3 / (S - 2)
         n_l = len(durs)
         D = depth_sum / n_l
         s_mean = statistics.mean(range(1, S - 1))
@@ -465,7 +480,8 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "launch_us": 1e6 * statistics.mean(durs), "launch_us_in_graph_no_flush": warm_us,
                 "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_tree": per_tree,
-                "mean_depth": D, "l2": "flushed before every timed launch (256 MiB write)"}
+                "mean_depth": D, "l2": "flushed before every timed launch (256 MiB write)",
+                "per_sim_us_flushed": [round(1e6 * d, 1) for d in durs[::6]], "max_depth": depth_max[::6]}
         # env kernel
         evs2 = []
         for _ in range(30):

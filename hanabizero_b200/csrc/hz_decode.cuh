@@ -70,7 +70,7 @@ __device__ __forceinline__ float warp_decode8(const Logits8& x, const float* __r
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     if (c0 + k < width) {
-      const float e = expf(x.v[k] - m);
+      const float e = __expf(x.v[k] - m);   // decode tolerance is float-level, not bit-level (network output)
       se += e;
       sw += e * support[c0 + k];
     }
