@@ -100,28 +100,34 @@ __device__ __forceinline__ void advance(uint8_t* st, int H) {  // hanabi_state.c
 
 // ApplyRandomChance (hanabi_state.cc:282-286): ChanceOutcomes (313-325) -> PickRandomChance
 // (hanabi_game.cc:106-112, libstdc++ discrete_distribution + generate_canonical<double,53>) ->
-// ApplyMove(kDeal) (221-243).  Warp-cooperative; all lanes must call.
+// ApplyMove(kDeal) (221-243).  Warp-cooperative; all lanes must call.  scratch: 64 doubles of shared
+// memory per warp.  The two ordered fp64 sums (std::accumulate, std::partial_sum) are evaluated in
+// libstdc++'s order, but by every lane on its own prefix of the compacted outcome list, so no
+// shuffle sits on the add chain.
 __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_t* mt, int& mti,
-                                            int lane) {
+                                            double* scratch, int lane) {
   const int n_types = g.C * g.R;
   const int cnt = lane < n_types ? st[O_DECKCNT + lane] : 0;
   const bool have = cnt > 0;
   const unsigned mask = __ballot_sync(HZ_FULL, have);
+  const int m = __popc(mask);
   int pick = __ffs(mask) - 1;  // single outcome: _M_prob.size() < 2 -> index 0, no draw consumed
-  if (__popc(mask) >= 2) {
-    const double w = have ? __ddiv_rn((double)cnt, (double)st[O_DECK]) : 0.0;  // ChanceOutcomeProb
+  if (m >= 2) {
+    const int pos = __popc(mask & ((1u << lane) - 1u));   // index of this lane's outcome in the list
+    double* w = scratch;        // [m] ChanceOutcomeProb
+    double* qn = scratch + 32;  // [m] normalised
+    const double wv = have ? __ddiv_rn((double)cnt, (double)st[O_DECK]) : 0.0;
+    if (have) w[pos] = wv;
+    __syncwarp();
     double sum = 0.0;  // std::accumulate ascending
-    for (unsigned m = mask; m; m &= m - 1) sum = __dadd_rn(sum, shfl_double(w, __ffs(m) - 1));
-    const double qn = have ? __ddiv_rn(w, sum) : 0.0;  // __normalize
-    double acc = 0.0, cp = 2.0;  // std::partial_sum ascending; lanes without an outcome never match
-    bool first = true;
-    const int last = 31 - __clz(mask);
-    for (unsigned m = mask; m; m &= m - 1) {
-      const int src = __ffs(m) - 1;
-      const double qv = shfl_double(qn, src);
-      acc = first ? qv : __dadd_rn(acc, qv);
-      first = false;
-      if (lane == src) cp = (src == last) ? 1.0 : acc;  // _M_cp.back() = 1.0
+    for (int i = 0; i < m; ++i) sum = __dadd_rn(sum, w[i]);
+    if (have) qn[pos] = __ddiv_rn(wv, sum);  // __normalize
+    __syncwarp();
+    double cp = 2.0;  // std::partial_sum ascending; lanes without an outcome never match
+    if (have) {
+      double acc = qn[0];
+      for (int i = 1; i <= pos; ++i) acc = __dadd_rn(acc, qn[i]);
+      cp = (pos == m - 1) ? 1.0 : acc;  // _M_cp.back() = 1.0
     }
     const uint32_t u0 = mt_draw(mt, mti, lane);
     const uint32_t u1 = mt_draw(mt, mti, lane);
@@ -130,6 +136,7 @@ __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_
     if (p >= 1.0) p = 0x1.fffffffffffffp-1;                                // nextafter(1, 0)
     const unsigned ge = __ballot_sync(HZ_FULL, have && cp >= p);           // std::lower_bound
     pick = __ffs(ge) - 1;
+    __syncwarp();
   }
   if (lane == 0) {
     const int to = player_to_deal(st, g.H);
@@ -265,84 +272,110 @@ __device__ __forceinline__ void new_state(uint8_t* st, const Rules& g, int lane)
   __syncwarp();
 }
 
-// bit i of CanonicalObservationEncoder::Encode (canonical_encoders.cc:441-463) for `obs`
+// ---- observation as a bit string ---------------------------------------------------------------
+// The global observation (rl_env.py:262,433) = EncodeOwnHand (canonical_encoders.cc:465-486) ‖
+// CanonicalObservationEncoder::Encode (441-463: hands 66-109, board 127-171, discards 192-215, last
+// action 240-342, card knowledge 370-423) ‖ turn one-hot (rl_env.py:256-257).  It is assembled as
+// ~44 bit-field segments OR-ed into shared-memory words (one or two segments per lane), then expanded
+// to float 0/1 with coalesced stores; the local observation is its suffix.
+__device__ __forceinline__ void or_bits(uint32_t* w, int bit, uint32_t v) {
+  if (v == 0u) return;
+  const int i = bit >> 5, sh = bit & 31;
+  atomicOr(&w[i], v << sh);
+  if (sh != 0 && (v >> (32 - sh)) != 0u) atomicOr(&w[i + 1], v >> (32 - sh));
+}
+__device__ __forceinline__ uint32_t ones(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
 template <int C, int R, int H, int MI, int ML>
-__device__ __forceinline__ bool enc_bit(const uint8_t* st, int obs, int i) {
-  constexpr int BPC = C * R;
-  constexpr int PER_COLOR = 3 + 2 * (R - 2) + 1;
-  constexpr int DECK_MAX = PER_COLOR * C;
-  constexpr int HANDS = (P - 1) * H * BPC;
-  const int other = (obs + 1) % P;
-  // hands :66-109
-  if (i < HANDS) {
-    const int k = i / BPC, ci = i - k * BPC;
-    return k < st[O_HLEN + other] && st[hand_off(other, k)] == ci;
-  }
-  i -= HANDS;
-  if (i < P) return st[O_HLEN + (obs + i) % P] < H;
-  i -= P;
-  // board :127-171
-  constexpr int DW = DECK_MAX - P * H;
-  if (i < DW) return i < st[O_DECK];
-  i -= DW;
-  if (i < BPC) {
-    const int c = i / R, r = i - c * R;
-    return st[O_FW + c] == r + 1;
-  }
-  i -= BPC;
-  if (i < MI) return i < st[O_INFO];
-  i -= MI;
-  if (i < ML) return i < st[O_LIFE];
-  i -= ML;
-  // discards :192-215 (per colour: ranks with 3,2,..,2,1 copies, thermometer each)
-  if (i < DECK_MAX) {
-    const int c = i / PER_COLOR, w = i - c * PER_COLOR;
-    const int r = w < 3 ? 0 : (w - 3) / 2 + 1;
-    const int idx = w < 3 ? w : (w - 3) - (r - 1) * 2;
-    return idx < st[O_DISC + c * R + r];
-  }
-  i -= DECK_MAX;
-  // last action :240-342
-  constexpr int LAST = P + 4 + P + C + R + H + H + BPC + 2;
-  if (i < LAST) {
-    if (!st[O_LMVALID]) return false;
+struct ObsLayout {
+  static constexpr int BPC = C * R, OWN = H * BPC;
+  static constexpr int PER_COLOR = 3 + 2 * (R - 2) + 1, DECK_MAX = PER_COLOR * C;
+  static constexpr int HANDS = (P - 1) * H * BPC, DW = DECK_MAX - P * H;
+  static constexpr int LAST_A = P + 4 + P + C + R + H + H, LAST = LAST_A + BPC + 2, PER_CARD = BPC + C + R;
+  static constexpr int o_hands = OWN, o_miss = o_hands + HANDS, o_deck = o_miss + P, o_fw = o_deck + DW;
+  static constexpr int o_info = o_fw + BPC, o_life = o_info + MI, o_disc = o_life + ML, o_last = o_disc + DECK_MAX;
+  static constexpr int o_know = o_last + LAST, o_turn = o_know + P * H * PER_CARD, GLOBAL = o_turn + P;
+  static constexpr int ENC = GLOBAL - OWN - P, WORDS = (GLOBAL + 31) / 32 + 1;
+  // segment table
+  static constexpr int s_own = 0, s_other = H, s_miss = 2 * H, s_deck = s_miss + 1, s_fw = s_deck + 2;
+  static constexpr int s_info = s_fw + 1, s_life = s_info + 1, s_disc = s_life + 1, s_last = s_disc + C;
+  static constexpr int s_know = s_last + 2, s_turn = s_know + 2 * P * H, SEGS = s_turn + 1;
+  static_assert(DW <= 64 && LAST_A <= 32 && BPC + 2 <= 32 && PER_COLOR <= 32, "segment wider than a word");
+};
+
+template <int C, int R, int H, int MI, int ML>
+__device__ __forceinline__ void obs_segment(const uint8_t* st, int cur, uint32_t* w, int seg) {
+  using L = ObsLayout<C, R, H, MI, ML>;
+  const int other = (cur + 1) % P;
+  if (seg < L::s_other) {  // own hand, slot k
+    const int k = seg;
+    if (k < st[O_HLEN + cur]) or_bits(w, k * L::BPC + st[hand_off(cur, k)], 1u);
+  } else if (seg < L::s_miss) {  // the other player's hand, slot k
+    const int k = seg - L::s_other;
+    if (k < st[O_HLEN + other]) or_bits(w, L::o_hands + k * L::BPC + st[hand_off(other, k)], 1u);
+  } else if (seg == L::s_miss) {  // "hand is short" bits, observer first
+    or_bits(w, L::o_miss, (st[O_HLEN + cur] < H ? 1u : 0u) | (st[O_HLEN + other] < H ? 2u : 0u));
+  } else if (seg < L::s_fw) {  // deck size thermometer (two words)
+    const int n = st[O_DECK];
+    if (seg == L::s_deck) or_bits(w, L::o_deck, ones(n < 32 ? n : 32));
+    else if (n > 32) or_bits(w, L::o_deck + 32, ones(n - 32));
+  } else if (seg == L::s_fw) {  // fireworks: one-hot of (height - 1) per colour
+    uint32_t v = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      if (st[O_FW + c] > 0) v |= 1u << (c * R + st[O_FW + c] - 1);
+    or_bits(w, L::o_fw, v);
+  } else if (seg == L::s_info) {
+    or_bits(w, L::o_info, ones(st[O_INFO]));
+  } else if (seg == L::s_life) {
+    or_bits(w, L::o_life, ones(st[O_LIFE]));
+  } else if (seg < L::s_last) {  // discards of colour c: thermometers of widths 3,2,..,2,1
+    const int c = seg - L::s_disc;
+    uint32_t v = ones(st[O_DISC + c * R]);
+#pragma unroll
+    for (int r = 1; r < R; ++r) v |= ones(st[O_DISC + c * R + r]) << (3 + 2 * (r - 1));
+    or_bits(w, L::o_disc + c * L::PER_COLOR, v);
+  } else if (seg < L::s_know) {  // last non-deal move (observer-relative)
+    if (!st[O_LMVALID]) return;
     const int ty = st[O_LMTYPE];
-    const int rel = (st[O_LMPLAYER] - obs + P) % P;
-    const bool reveal = ty == MV_REVEAL_COLOR || ty == MV_REVEAL_RANK;
-    const bool pd = ty == MV_PLAY || ty == MV_DISCARD;
-    if (i < P) return i == rel;
-    i -= P;
-    if (i < 4) return i == (ty == MV_PLAY ? 0 : ty == MV_DISCARD ? 1 : ty == MV_REVEAL_COLOR ? 2 : 3);
-    i -= 4;
-    if (i < P) return reveal && i == (rel + st[O_LMTGT]) % P;
-    i -= P;
-    if (i < C) return ty == MV_REVEAL_COLOR && i == st[O_LMCOLOR];
-    i -= C;
-    if (i < R) return ty == MV_REVEAL_RANK && i == st[O_LMRANK];
-    i -= R;
-    if (i < H) return reveal && ((st[O_LMREVEAL] >> i) & 1);
-    i -= H;
-    if (i < H) return pd && i == st[O_LMIDX];
-    i -= H;
-    if (i < BPC) return pd && i == st[O_LMCARD];
-    i -= BPC;
-    return ty == MV_PLAY && ((st[O_LMFLAGS] >> i) & 1);
+    const bool reveal = ty == MV_REVEAL_COLOR || ty == MV_REVEAL_RANK, pd = ty == MV_PLAY || ty == MV_DISCARD;
+    if (seg == L::s_last) {
+      const int rel = (st[O_LMPLAYER] - cur + P) % P;
+      uint32_t v = 1u << rel;
+      v |= 1u << (P + (ty == MV_PLAY ? 0 : ty == MV_DISCARD ? 1 : ty == MV_REVEAL_COLOR ? 2 : 3));
+      if (reveal) v |= 1u << (P + 4 + (rel + st[O_LMTGT]) % P);
+      if (ty == MV_REVEAL_COLOR) v |= 1u << (P + 4 + P + st[O_LMCOLOR]);
+      if (ty == MV_REVEAL_RANK) v |= 1u << (P + 4 + P + C + st[O_LMRANK]);
+      if (reveal) v |= (uint32_t)(st[O_LMREVEAL] & ((1 << H) - 1)) << (P + 4 + P + C + R);
+      if (pd) v |= 1u << (P + 4 + P + C + R + H + st[O_LMIDX]);
+      or_bits(w, L::o_last, v);
+    } else {
+      uint32_t v = 0;
+      if (pd) v |= 1u << st[O_LMCARD];
+      if (ty == MV_PLAY) v |= (uint32_t)(st[O_LMFLAGS] & 3) << L::BPC;
+      or_bits(w, L::o_last + L::LAST_A, v);
+    }
+  } else if (seg < L::s_turn) {  // card knowledge: player rel, slot k; part 0 = plausible grid, 1 = hints
+    const int idx = (seg - L::s_know) >> 1, part = (seg - L::s_know) & 1;
+    const int rel = idx / H, k = idx - rel * H, p = (cur + rel) % P;
+    if (k >= st[O_HLEN + p]) return;
+    const int o = hand_off(p, k), base = L::o_know + idx * L::PER_CARD;
+    if (part == 0) {
+      uint32_t v = 0;
+      const uint32_t rm = st[o + 2];
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if ((st[o + 1] >> c) & 1) v |= rm << (c * R);
+      or_bits(w, base, v);
+    } else {
+      uint32_t v = 0;
+      if (st[o + 3] != kNone) v |= 1u << st[o + 3];
+      if (st[o + 4] != kNone) v |= 1u << (C + st[o + 4]);
+      or_bits(w, base + L::BPC, v);
+    }
+  } else if (seg == L::s_turn) {
+    or_bits(w, L::o_turn, 1u << cur);
   }
-  i -= LAST;
-  // card knowledge :370-423
-  constexpr int PER_CARD = BPC + C + R;
-  const int rel = i / (H * PER_CARD);
-  i -= rel * (H * PER_CARD);
-  const int k = i / PER_CARD, f = i - k * PER_CARD;
-  const int p = (obs + rel) % P;
-  if (k >= st[O_HLEN + p]) return false;
-  const int o = hand_off(p, k);
-  if (f < BPC) {
-    const int c = f / R, r = f - c * R;
-    return ((st[o + 1] >> c) & 1) && ((st[o + 2] >> r) & 1);
-  }
-  if (f < BPC + C) return st[o + 3] == f - BPC;
-  return st[o + 4] == f - BPC - C;
 }
 
 struct EnvView {
@@ -372,12 +405,16 @@ struct EnvArgs {
 
 template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
 __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs a) {
+  using L = ObsLayout<C, R, H, MI, ML>;
   __shared__ uint32_t s_state[kEnvWarps][kStateBytes / 4];
+  __shared__ double s_scratch[kEnvWarps][64];
+  __shared__ uint32_t s_obs[kEnvWarps][L::WORDS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = blockIdx.x * kEnvWarps + warp;
   if (gi >= ev.N) return;
   const Rules& g = ev.g;
   uint8_t* st = reinterpret_cast<uint8_t*>(s_state[warp]);
+  double* scratch = s_scratch[warp];
   uint32_t* gstate = reinterpret_cast<uint32_t*>(ev.state + (size_t)gi * kStateBytes);
   uint32_t* mt = ev.mt + (size_t)gi * 624;
   s_state[warp][lane] = gstate[lane];
@@ -388,7 +425,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
 
   if (RESET && (a.reset_mask == nullptr || a.reset_mask[gi])) {  // rl_env.py:249-252
     new_state(st, g, lane);
-    while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, lane);
+    while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, scratch, lane);
     dirty = true;
   }
   if (STEP && (a.active == nullptr || a.active[gi])) {  // rl_env.py:413-438
@@ -401,14 +438,14 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
       const int last_score = score;
       if (lane == 0) apply_move(st, g, action);
       __syncwarp();
-      while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, lane);
+      while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, scratch, lane);
       score = score_of(st, C);
       reward = score - last_score;
       done = is_terminal(st, g);
       dirty = true;
       if (done && a.auto_reset) {
         new_state(st, g, lane);
-        while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, lane);
+        while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, scratch, lane);
       }
     }
     if (lane == 0) {
@@ -423,27 +460,23 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
     if (lane == 0 && mti != mti0) ev.mti[gi] = mti;
   }
   if (OBSERVE) {
-    constexpr int BPC = C * R, OWN = H * BPC;
-    constexpr int ENC = ((P - 1) * H * BPC + P) + ((3 + 2 * (R - 2) + 1) * C - P * H + BPC + MI + ML) +
-                        (3 + 2 * (R - 2) + 1) * C + (P + 4 + P + C + R + H + H + BPC + 2) +
-                        P * H * (BPC + C + R);
-    constexpr int GLOBAL = OWN + ENC + P;
+    constexpr int BPC = C * R;
     const int cur = (int8_t)st[O_CUR];
+    uint32_t* words = s_obs[warp];
+    for (int i = lane; i < L::WORDS; i += HZ_WARP) words[i] = 0u;
+    __syncwarp();
+    for (int seg = lane; seg < L::SEGS; seg += HZ_WARP) obs_segment<C, R, H, MI, ML>(st, cur, words, seg);
+    __syncwarp();
     float* og = a.out_global ? a.out_global + (size_t)gi * a.ld_global : nullptr;
     float* ol = a.out_local ? a.out_local + (size_t)gi * a.ld_local : nullptr;
-    for (int j = lane; j < GLOBAL; j += HZ_WARP) {
-      bool bit;
-      if (j < OWN) {  // EncodeOwnHand canonical_encoders.cc:465-486
-        const int k = j / BPC, ci = j - k * BPC;
-        bit = k < st[O_HLEN + cur] && st[hand_off(cur, k)] == ci;
-      } else if (j < OWN + ENC) {
-        bit = enc_bit<C, R, H, MI, ML>(st, cur, j - OWN);
-      } else {
-        bit = (j - OWN - ENC) == cur;  // agent_turn one-hot rl_env.py:256-257,429-430
+#pragma unroll 5
+    for (int it = 0; it < (L::GLOBAL + 31) / 32; ++it) {
+      const int j = it * 32 + lane;
+      const float v = ((words[it] >> lane) & 1u) ? 1.0f : 0.0f;
+      if (j < L::GLOBAL) {
+        if (og) og[j] = v;
+        if (ol && j >= L::OWN) ol[j - L::OWN] = v;
       }
-      const float v = bit ? 1.0f : 0.0f;
-      if (og) og[j] = v;
-      if (ol && j >= OWN) ol[j - OWN] = v;
     }
     if (a.out_legal && lane < g.A) {
       a.out_legal[(size_t)gi * g.A + lane] = move_is_legal(st, g, lane) ? 1.0f : 0.0f;
