@@ -180,28 +180,33 @@ def run_reference(args):
 # our arm
 # ======================================================================================================
 class ClockSampler(threading.Thread):
+    """One long-running `nvidia-smi -lms 100` for the whole timed phase (the recipe's clocks line)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.samples, self.proc = index, [], None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
                 if len(parts) >= 7:
                     self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        except Exception:
+            pass
 
     def stop(self):
-        self._stop_evt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         self.join(timeout=3)
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         reasons = set()
@@ -212,6 +217,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": float(self.samples[0][1]) if self.samples else None,
                 "samples": len(self.samples), "reasons": sorted(reasons)}
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the
+    committed `ncu --set full` capture (profiles/); None if the summary is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_k_search_step.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if "1, 1" in r[ik]]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -288,6 +309,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)   # let nvidia-smi attach before the timed regions
     # ---- timed region 1: device-resident search ------------------------------------------------
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -477,7 +499,8 @@ def run_ours(args):
         bytes_launch = N * per_tree
         achieved = bytes_launch / statistics.mean(durs) / 1e9
         roof = {"bound": "hbm", "kernel": "k_search_step<half,backprop,traverse> (hz_trees_search_step)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic_per_launch(),
                 "peak_source": peak_src, "launch_us": 1e6 * statistics.mean(durs), "launch_us_in_graph_no_flush": warm_us,
                 "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_tree": per_tree,
                 "mean_depth": D, "l2": "flushed before every timed launch (256 MiB write)",

@@ -52,6 +52,8 @@ SIGNATURES = {
     "hz_gather_hidden": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "hz_support_decode": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i64, _f]),
     "hz_bias_act": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i]),
+    "hz_select_action": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "hz_stack_push": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i]),
     "hz_envs_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp]),
     "hz_envs_destroy": (_i, [_vp]),
     "hz_envs_dims": (_i, [_vp, _vp]),

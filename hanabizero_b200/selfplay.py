@@ -1,0 +1,127 @@
+"""Device-resident self-play step — the "next" rows of the scope table that sit
+between the two halves of the hot path in the reference's actor loop
+(/root/reference/core/selfplay_worker.py:258-300):
+
+    stack_obs -> initial_inference -> Roots.prepare(noise) -> MCTS.run_multi -> select_action -> env.step
+
+`select_action` is the drop-in for core/utils.py:280-295; `SelfPlayEngine` chains everything for N games
+without a host hop: the frame stack (core/game.py:169-174) lives in HBM, the env kernel writes each new
+observation straight into it, actions go from the sampler kernel into the env kernel.
+"""
+import numpy as np
+import torch
+
+from . import _lib, cytree
+from ._lib import check, ptr
+from .hanabi_env import HanabiVecEnv
+from .mcts import MCTS
+
+
+def select_action_batch(visit_counts, legal_actions, temperature=1.0, deterministic=True, uniforms=None):
+    """Batched select_action on the device.  visit_counts int32 [N, A] CUDA (illegal entries are zeroed
+    in place, as the reference mutates its argument), legal_actions float [N, A].  Non-deterministic
+    sampling consumes `uniforms` (float64 [N] in [0, 1); drawn with torch if omitted) through
+    numpy.random.choice's inverse-CDF rule.  Returns (actions int32 [N], entropies float32 [N])."""
+    n, a = visit_counts.shape
+    dev = visit_counts.device
+    lib = _lib.load()
+    legal = legal_actions.to(device=dev, dtype=torch.float32).contiguous()
+    temp = None
+    if not (isinstance(temperature, (int, float)) and float(temperature) == 1.0):
+        temp = torch.as_tensor(temperature, dtype=torch.float32, device=dev).expand(n).contiguous()
+    if deterministic:
+        uni = None
+    else:
+        uni = (torch.rand(n, dtype=torch.float64, device=dev) if uniforms is None
+               else torch.as_tensor(uniforms, dtype=torch.float64, device=dev).contiguous())
+    actions = torch.empty(n, dtype=torch.int32, device=dev)
+    entropy = torch.empty(n, dtype=torch.float32, device=dev)
+    check(lib.hz_select_action(torch.cuda.current_stream(dev).cuda_stream, ptr(visit_counts), ptr(legal), ptr(temp),
+                               ptr(uni), n, a, ptr(actions), ptr(entropy)))
+    return actions, entropy
+
+
+def select_action(visit_counts, temperature=1, deterministic=True, legal_actions=None):
+    """core/utils.py:280-295 for one root: returns (action_pos, count_entropy)."""
+    assert legal_actions is not None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    v = torch.as_tensor(np.asarray(visit_counts), dtype=torch.int32, device=dev).view(1, -1).contiguous()
+    lg = torch.as_tensor(np.asarray(legal_actions, dtype=np.float32), device=dev).view(1, -1)
+    uni = None if deterministic else np.random.random(1)
+    a, e = select_action_batch(v, lg, float(temperature), deterministic, uni)
+    zeroed = v[0].cpu().tolist()
+    for i, c in enumerate(zeroed):          # the reference mutates the caller's list
+        try:
+            visit_counts[i] = c
+        except TypeError:
+            break
+    return int(a.item()), float(e.item())
+
+
+class SelfPlayEngine:
+    """N Hanabi games + N trees advanced one move per `step()` entirely on one GPU."""
+
+    def __init__(self, num_games, hanabi_name, model, config, seeds=None, mdp="global", stack=4, device=None):
+        self.env = HanabiVecEnv(num_games, hanabi_name, seeds, device=device)
+        self.dev, self.n, self.stack, self.mdp = self.env.device, num_games, int(stack), mdp
+        self.model, self.config, self.mcts = model, config, MCTS(config)
+        self.obs_dim = self.env.global_dim if mdp == "global" else self.env.local_dim
+        self.frames = torch.zeros(num_games, self.stack, self.obs_dim, device=self.dev)
+        self.legal = torch.zeros(num_games, self.env.num_actions, device=self.dev)
+        self.lib = _lib.load()
+        self._obs = torch.zeros(num_games, self.obs_dim, device=self.dev)
+        self._all_done = torch.ones(num_games, dtype=torch.uint8, device=self.dev)
+        alpha = float(getattr(config, "root_dirichlet_alpha", 0.3))
+        self._gamma = torch.distributions.Gamma(torch.full((num_games, self.env.num_actions), alpha, device=self.dev),
+                                                torch.ones((), device=self.dev))
+
+    def _observe_into(self):
+        g, l = (self._obs, None) if self.mdp == "global" else (None, self._obs)
+        return g, l
+
+    def _push(self, done):
+        check(self.lib.hz_stack_push(torch.cuda.current_stream(self.dev).cuda_stream, ptr(self.frames), ptr(self._obs),
+                                     self._obs.stride(0), ptr(done), self.n, self.stack, self.obs_dim))
+
+    def reset(self):
+        """env.reset() for every game; the first observation fills the whole stack (selfplay_worker.py:137)."""
+        self.env.reset_all(observe=False)
+        g, l = self._observe_into()
+        check(self.lib.hz_envs_observe(self.env._h, torch.cuda.current_stream(self.dev).cuda_stream, ptr(g),
+                                       0 if g is None else g.stride(0), ptr(l), 0 if l is None else l.stride(0),
+                                       ptr(self.legal)))
+        self._push(self._all_done)
+        return self.frames.view(self.n, -1), self.legal
+
+    @torch.no_grad()
+    def step(self, temperature=1.0, deterministic=False, noise=True):
+        """One self-play move for every game.  Returns a dict of CUDA tensors."""
+        cfg, n = self.config, self.n
+        amp = getattr(cfg, "amp_type", "none") == "torch_amp"
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            _, logits, hidden = self.model.initial_inference_device(self.frames.view(n, -1))
+        roots = cytree.Roots(n, self.env.num_actions, cfg.num_simulations, device=self.dev)
+        zeros = torch.zeros(n, device=self.dev)
+        legal_i = self.legal.int()
+        if noise:   # np.random.dirichlet([alpha] * A) per root (selfplay_worker.py:279), drawn on the device
+            gam = self._gamma.sample()
+            nz = gam / gam.sum(1, keepdim=True)
+            roots.prepare(cfg.root_exploration_fraction, nz, zeros, logits.float(), legal_i)
+        else:
+            roots.prepare_no_noise(zeros, logits.float(), legal_i)
+        self.mcts.run_multi(roots, self.model, hidden)
+        visits, values = roots.get_stats_tensors()
+        actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
+        g, l = self._observe_into()
+        _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=True, out_global=g, out_local=l,
+                                                         out_legal=self.legal, want_local=l is not None) \
+            if g is not None else self._step_local(actions)
+        self._push(done)
+        return dict(action=actions, reward=reward.clone(), done=done.clone(), score=score.clone(), visits=visits,
+                    root_value=values, entropy=entropy)
+
+    def _step_local(self, actions):
+        e = self.env
+        check(e._lib.hz_envs_step_observe(e._h, e._stream(), ptr(actions), None, 1, ptr(e.reward), ptr(e.done),
+                                          ptr(e.score), None, 0, ptr(self._obs), self._obs.stride(0), ptr(self.legal)))
+        return None, None, None, e.reward, e.done, e.score

@@ -213,6 +213,22 @@ int hz_bias_act(void* stream, void* out, int64_t ld_out, const void* x, int64_t 
                 const void* residual, int64_t ld_res, const void* table, const int64_t* idx,
                 int rows, int cols, int relu, int elem_bytes);
 
+/* ------------------------------------------------------------------------------------------
+ * "Next" rows: the hops between a search and the next env step.
+ * ------------------------------------------------------------------------------------------ */
+/* select_action (/root/reference/core/utils.py:280-295): visits int32[N][A] (dev; counts of illegal
+ * actions are zeroed in place like the reference does), legal float[N][A], temperature float[N] or
+ * NULL (= 1), uniforms double[N] in [0,1) or NULL (deterministic: first arg-max).  Sampling follows
+ * numpy.random.choice (cdf = cumsum(p)/sum, searchsorted side='right') for the given uniform.
+ * out_action int32[N], out_entropy float[N] or NULL (base-2 entropy of the visit distribution). */
+int hz_select_action(void* stream, int32_t* visits, const float* legal, const float* temperature,
+                     const double* uniforms, int num, int num_actions, int32_t* out_action, float* out_entropy);
+/* Frame stack on the device (core/game.py:169-174): stack float[N][depth][dim] shifts left by one
+ * frame and appends obs[i] (row stride ld_obs); where done[i] != 0 every slot is filled with obs[i]
+ * (first frame of the next episode replicated, selfplay_worker.py:137). */
+int hz_stack_push(void* stream, float* stack, const float* obs, int64_t ld_obs, const uint8_t* done, int num,
+                  int stack_depth, int dim);
+
 /* A fixed chain of nn.Linear-shaped GEMMs executed with cuBLASLt, one launch each:
  *   D[m][n] = act( A[m][k] . W[n][k]^T + bias[n] + C[m][n] ),  all row-major, strided batches allowed.
  * Pointers are captured at creation (static buffers: the chain is CUDA-graph friendly). */

@@ -1,0 +1,103 @@
+"""GPU: the "next" rows — device select_action, frame stack, and the device-resident
+self-play step that chains env + network + search without a host hop."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_select_action(visit_counts, temperature, deterministic, legal_actions, u):
+    """core/utils.py:280-295 with np.random.choice replaced by its own algorithm for a given uniform u."""
+    visit_counts = list(visit_counts)
+    for i in range(len(legal_actions)):
+        if legal_actions[i] == 0 and visit_counts[i] >= 1:
+            visit_counts[i] = 0
+    probs = [float(v) ** (1 / temperature) for v in visit_counts]
+    total = sum(probs)
+    probs = [x / total for x in probs]
+    if deterministic:
+        action = int(np.argmax(visit_counts))
+    else:
+        cdf = np.cumsum(np.asarray(probs, np.float64))
+        cdf /= cdf[-1]
+        action = int(np.searchsorted(cdf, u, side="right"))
+    pk = np.asarray(probs, np.float64)
+    pk = pk / pk.sum()
+    ent = float(-(pk[pk > 0] * np.log(pk[pk > 0])).sum() / np.log(2))
+    return action, ent, visit_counts
+
+
+@pytest.mark.parametrize("temperature", [1.0, 0.5, 0.25])
+@pytest.mark.parametrize("deterministic", [True, False])
+def test_select_action_matches_reference_rule(temperature, deterministic):
+    from hanabizero_b200.selfplay import select_action_batch
+    rng = np.random.default_rng(3)
+    N, A = 512, 20
+    visits = rng.integers(0, 50, (N, A)).astype(np.int32)
+    visits[rng.random((N, A)) < 0.5] = 0
+    visits[np.arange(N), rng.integers(0, A, N)] += 1
+    legal = (rng.random((N, A)) < 0.7).astype(np.float32)
+    legal[np.arange(N), visits.argmax(1)] = 1.0
+    u = rng.random(N)
+    v_dev = torch.from_numpy(visits.copy()).cuda()
+    act, ent = select_action_batch(v_dev, torch.from_numpy(legal).cuda(), temperature, deterministic, u)
+    act, ent, v_after = act.cpu().numpy(), ent.cpu().numpy(), v_dev.cpu().numpy()
+    for i in range(N):
+        a, e, vc = ref_select_action(visits[i], temperature, deterministic, legal[i], u[i])
+        assert act[i] == a, (i, act[i], a)
+        assert abs(ent[i] - e) <= 1e-5 * max(1.0, abs(e))        # fp64 on both sides, float32 output
+        assert (v_after[i] == np.asarray(vc)).all()               # illegal counts zeroed in place
+
+
+def test_select_action_scalar_dropin():
+    from hanabizero_b200.selfplay import select_action
+    counts = [0, 3, 40, 5, 1]
+    a, e = select_action(counts, temperature=1, deterministic=True, legal_actions=[1, 1, 0, 1, 1])
+    assert a == 3 and counts[2] == 0 and e > 0
+
+
+def test_stack_push_matches_torch():
+    from hanabizero_b200 import _lib
+    lib = _lib.load()
+    N, S, D = 37, 4, 785
+    stack = torch.rand(N, S, D, device="cuda")
+    obs = torch.rand(N, D + 3, device="cuda")
+    done = (torch.rand(N, device="cuda") < 0.3).to(torch.uint8)
+    want = torch.cat((stack[:, 1:], obs[:, None, :D]), dim=1)
+    want[done.bool()] = obs[done.bool()][:, None, :D].expand(-1, S, -1)
+    _lib.check(lib.hz_stack_push(torch.cuda.current_stream().cuda_stream, stack.data_ptr(), obs.data_ptr(), obs.stride(0),
+                                 done.data_ptr(), N, S, D))
+    assert torch.equal(stack, want)
+
+
+@pytest.mark.parametrize("mdp", ["global", "local"])
+def test_selfplay_engine_steps_on_device(mdp):
+    from hanabizero_b200.mcts import SearchConfig
+    from hanabizero_b200.model import MuZeroNetFull
+    from hanabizero_b200.selfplay import SelfPlayEngine
+    N, S, stack = 128, 12, 4
+    torch.manual_seed(0)
+    dim = 785 if mdp == "global" else 660
+    model = MuZeroNetFull(dim * stack, 20).randomize_heads().cuda().eval()
+    eng = SelfPlayEngine(N, "Hanabi-Full", model, SearchConfig(num_simulations=S), seeds=np.arange(N), mdp=mdp, stack=stack)
+    obs, legal = eng.reset()
+    assert obs.shape == (N, dim * stack)
+    assert torch.equal(eng.frames[:, 0], eng.frames[:, -1])       # first frame replicated
+    total_done = 0
+    for t in range(8):
+        legal_before = eng.legal.clone()
+        prev_last = eng.frames[:, -1].clone()
+        out = eng.step(temperature=1.0, deterministic=(t % 2 == 0))
+        a = out["action"].long()
+        assert (legal_before.gather(1, a[:, None]) == 1).all()    # only legal moves are played
+        assert (out["visits"].sum(1) == S - 1).all()
+        d = out["done"].bool()
+        total_done += int(d.sum())
+        # frame stack: shifted for running games, refilled for restarted ones
+        assert torch.equal(eng.frames[~d][:, -2], prev_last[~d])
+        if d.any():
+            assert torch.equal(eng.frames[d][:, 0], eng.frames[d][:, -1])
+        ref_obs = eng.env.observe()[0 if mdp == "global" else 1]
+        assert torch.equal(eng.frames[:, -1], ref_obs)
+    eng.env.check()
