@@ -29,6 +29,42 @@ __device__ __constant__ uint64_t k_exp2f_tab[32] = {
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull,
 };
 
+// Warp-cooperative variant: every lane must call.  The 32-entry table is held one entry per lane and
+// fetched with two shuffles — a per-lane index into __constant__ memory would serialise into up to 32
+// constant-cache replays.
+__device__ __forceinline__ float expf_glibc(float x);
+__device__ __forceinline__ float expf_glibc_warp(float x, int lane) {
+  const double N = 32.0;
+  const double InvLn2N = 0x1.71547652b82fep+0 * N;
+  const double SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / N / N / N;
+  const double C1 = 0x1.ebfce50fac4f3p-3 / N / N;
+  const double C2 = 0x1.62e42ff0c52d6p-1 / N;
+  const uint64_t my_tab = k_exp2f_tab[lane];   // uniform-stride read: one constant-cache pass
+  const uint32_t ux = __float_as_uint(x);
+  const uint32_t abstop = (ux >> 20) & 0x7ffu;
+  const double xd = (double)x;
+  const double z = __dmul_rn(InvLn2N, xd);
+  double kd = __dadd_rn(z, SHIFT);
+  const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, SHIFT);
+  const double r = __fma_rn(InvLn2N, xd, -kd);
+  const int src = (int)(ki & 31u);
+  const uint32_t tlo = __shfl_sync(0xffffffffu, (uint32_t)my_tab, src);
+  const uint32_t thi = __shfl_sync(0xffffffffu, (uint32_t)(my_tab >> 32), src);
+  uint64_t tt = ((uint64_t)thi << 32) | tlo;
+  tt += ki << 47;
+  const double s = __longlong_as_double((long long)tt);
+  const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
+  const double r2 = __dmul_rn(r, r);
+  double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+  y = __dadd_rn(__dmul_rn(zz, r2), y);
+  y = __dmul_rn(y, s);
+  float res = __double2float_rn(y);
+  if (abstop >= 0x42bu) res = expf_glibc(x);   // |x| >= 88, inf, NaN: the scalar routine's special cases
+  return res;
+}
+
 __device__ __forceinline__ float expf_glibc(float x) {
   const double N = 32.0;
   const double InvLn2N = 0x1.71547652b82fep+0 * N;
