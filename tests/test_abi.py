@@ -60,3 +60,17 @@ def test_product_code_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/_ref" not in text and "liboracle" not in text, f
+
+
+def test_dropin_import_paths_resolve_to_the_b200_modules():
+    """dropin/ first on PYTHONPATH: the reference's own import lines reach hanabizero_b200."""
+    import subprocess
+    import sys
+    code = ("import core.ctree.cytree as tree; from core.mcts import MCTS; from envs import HanabiEnv; "
+            "from envs.hanabi.rl_env import HanabiEnv as H2; "
+            "from config.hanabi_control.env_wrapper import HanabiControlWrapper; "
+            "from config.hanabi_control.model import MuZeroNetFull; "
+            "assert tree.Roots.__module__ == 'hanabizero_b200.cytree' and MCTS.__module__ == 'hanabizero_b200.mcts'; "
+            "assert HanabiEnv is H2 and hasattr(tree, 'multi_traverse') and hasattr(tree, 'batch_traverse')")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT]))
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd="/tmp")
