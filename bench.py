@@ -281,7 +281,7 @@ def run_ours(args):
     packed = torch.empty(world * N, A + 1, dtype=torch.int32, device=dev) if world > 1 else None
 
     mcts = MCTS(cfg)
-    launches_before = _lib.launch_count()
+    launches_before, gemm_before = _lib.launch_count(), _lib.gemm_launch_count()
 
     def search_step(roots_holder):
         roots = cytree.Roots(N, A, S, device=dev)
@@ -297,6 +297,7 @@ def run_ours(args):
     search_step(holder)                       # eager search (also the launch census)
     torch.cuda.synchronize()
     launches_per_search = _lib.launch_count() - launches_before
+    gemm_per_search = _lib.gemm_launch_count() - gemm_before
     for _ in range(W):
         search_step(holder)
     torch.cuda.synchronize()
@@ -547,6 +548,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_search * K),
             "gpu_launches_per_search": int(launches_per_search),
+            "library_gemm_launches_per_search": int(gemm_per_search),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "env": {"metric": "hanabi_env_steps_per_sec", "value": env_value, "unit": "steps/s",
                     "e2e": {"value": env_e2e, "unit": "steps/s", "h2d_bytes_per_step": 4 * N,

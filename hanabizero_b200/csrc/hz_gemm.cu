@@ -41,6 +41,8 @@ static size_t align_of(const void* p, int64_t ld_elems, int elem_bytes) {
 
 using namespace hz;
 
+static std::atomic<int64_t> g_gemm_launches{0};
+
 struct hz_gemm_plan {
   int device = 0, elem_bytes = 2;
   cublasLtHandle_t lt = nullptr;
@@ -209,6 +211,8 @@ int hz_gemm_plan_destroy(hz_gemm_plan* p) {
   return HZ_OK;
 }
 
+int64_t hz_gemm_launch_count(void) { return g_gemm_launches.load(); }
+
 int hz_gemm_plan_steps(const hz_gemm_plan* p) { return p ? (int)p->steps.size() : 0; }
 
 int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count) {
@@ -223,7 +227,7 @@ int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count) {
     const hz_gemm_step& s = st.s;
     HZ_LT(cublasLtMatmul(p->lt, st.op, &alpha, s.w, st.la, s.a, st.lb, &st.beta, s.c ? s.c : s.d, st.lc, s.d, st.ld,
                          &st.algo, p->workspace, p->ws_bytes, (cudaStream_t)stream));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_gemm_launches.fetch_add(1, std::memory_order_relaxed);
   }
   return HZ_OK;
 }

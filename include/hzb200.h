@@ -244,6 +244,9 @@ typedef struct hz_gemm_plan hz_gemm_plan;
 int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz_gemm_step* steps, int n_steps); /* sync */
 int hz_gemm_plan_destroy(hz_gemm_plan* p);                                                                     /* sync */
 int hz_gemm_plan_steps(const hz_gemm_plan* p);
+/* cuBLASLt launches issued through hz_gemm_plan_run in this process (library GEMMs, counted apart from
+ * hz_launch_count, which counts this library's own kernels) */
+int64_t hz_gemm_launch_count(void);
 int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count);
 
 #ifdef __cplusplus
