@@ -63,12 +63,34 @@ __device__ __forceinline__ void mt_refill(uint32_t* mt, int lane) {
   }
 }
 
-__device__ __forceinline__ uint32_t mt_draw(uint32_t* mt, int& mti, int lane) {
+// The next 32 raw state words are fetched once per kernel (one coalesced load, lane i holds
+// mt[start + i]); draws inside that window come from a shuffle instead of a dependent global load.
+struct MtWindow {
+  uint32_t word;   // this lane's prefetched state word
+  int start;       // index of lane 0's word; < 0 once a refill invalidated the window
+};
+
+__device__ __forceinline__ MtWindow mt_prefetch(const uint32_t* mt, int mti, int lane) {
+  MtWindow w;
+  w.start = mti;
+  w.word = (mti + lane < 624) ? mt[mti + lane] : 0u;
+  return w;
+}
+
+__device__ __forceinline__ uint32_t mt_draw(uint32_t* mt, int& mti, MtWindow& win, int lane) {
   if (mti >= 624) {
     mt_refill(mt, lane);
     mti = 0;
+    win.start = -1;
   }
-  uint32_t z = mt[mti++];
+  uint32_t z;
+  const int off = mti - win.start;
+  if (win.start >= 0 && off >= 0 && off < HZ_WARP) {   // warp-uniform
+    z = __shfl_sync(HZ_FULL, win.word, off);
+  } else {
+    z = mt[mti];
+  }
+  ++mti;
   z ^= (z >> 11);
   z ^= (z << 7) & 0x9d2c5680u;
   z ^= (z << 15) & 0xefc60000u;
@@ -104,7 +126,7 @@ __device__ __forceinline__ void advance(uint8_t* st, int H) {  // hanabi_state.c
 // memory per warp.  The two ordered fp64 sums (std::accumulate, std::partial_sum) are evaluated in
 // libstdc++'s order, but by every lane on its own prefix of the compacted outcome list, so no
 // shuffle sits on the add chain.
-__device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_t* mt, int& mti,
+__device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_t* mt, int& mti, MtWindow& win,
                                             double* scratch, int lane) {
   const int n_types = g.C * g.R;
   const int cnt = lane < n_types ? st[O_DECKCNT + lane] : 0;
@@ -129,8 +151,8 @@ __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_
       for (int i = 1; i <= pos; ++i) acc = __dadd_rn(acc, qn[i]);
       cp = (pos == m - 1) ? 1.0 : acc;  // _M_cp.back() = 1.0
     }
-    const uint32_t u0 = mt_draw(mt, mti, lane);
-    const uint32_t u1 = mt_draw(mt, mti, lane);
+    const uint32_t u0 = mt_draw(mt, mti, win, lane);
+    const uint32_t u1 = mt_draw(mt, mti, win, lane);
     double p = __dadd_rn((double)u0, __dmul_rn((double)u1, 4294967296.0));
     p = __dmul_rn(p, 5.421010862427522170037264004349708557128906250e-20);  // / 2^64 (exact)
     if (p >= 1.0) p = 0x1.fffffffffffffp-1;                                // nextafter(1, 0)
@@ -412,7 +434,8 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gi = blockIdx.x * kEnvWarps + warp;
   if (gi >= ev.N) return;
-  const Rules& g = ev.g;
+  // the rules as compile-time constants (the helpers are force-inlined, so divisions by R, C fold away)
+  const Rules g{C, R, H, MI, ML, 2 * H + (P - 1) * C + (P - 1) * R, L::ENC, L::OWN, L::DECK_MAX};
   uint8_t* st = reinterpret_cast<uint8_t*>(s_state[warp]);
   double* scratch = s_scratch[warp];
   uint32_t* gstate = reinterpret_cast<uint32_t*>(ev.state + (size_t)gi * kStateBytes);
@@ -420,12 +443,13 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
   s_state[warp][lane] = gstate[lane];
   int mti = ev.mti[gi];
   const int mti0 = mti;
+  MtWindow win = mt_prefetch(mt, mti, lane);
   __syncwarp();
   bool dirty = false;
 
   if (RESET && (a.reset_mask == nullptr || a.reset_mask[gi])) {  // rl_env.py:249-252
     new_state(st, g, lane);
-    while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, scratch, lane);
+    while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, win, scratch, lane);
     dirty = true;
   }
   if (STEP && (a.active == nullptr || a.active[gi])) {  // rl_env.py:413-438
@@ -438,14 +462,14 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
       const int last_score = score;
       if (lane == 0) apply_move(st, g, action);
       __syncwarp();
-      while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, scratch, lane);
+      while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, win, scratch, lane);
       score = score_of(st, C);
       reward = score - last_score;
       done = is_terminal(st, g);
       dirty = true;
       if (done && a.auto_reset) {
         new_state(st, g, lane);
-        while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, scratch, lane);
+        while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, win, scratch, lane);
       }
     }
     if (lane == 0) {
@@ -478,8 +502,21 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
         if (ol && j >= L::OWN) ol[j - L::OWN] = v;
       }
     }
-    if (a.out_legal && lane < g.A) {
-      a.out_legal[(size_t)gi * g.A + lane] = move_is_legal(st, g, lane) ? 1.0f : 0.0f;
+    if (a.out_legal) {
+      // LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all uids at once: lanes first agree on
+      // which colours / ranks the partner's hand holds, then each lane tests its own move id
+      const int other = (cur + 1) % P, n_me = st[O_HLEN + cur], n_ot = st[O_HLEN + other];
+      const int card = lane < n_ot ? st[hand_off(other, lane)] : -1;
+      const unsigned cmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card / R) : 0u);
+      const unsigned rmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card % R) : 0u);
+      if (lane < g.A) {
+        bool ok;
+        if (lane < H) ok = st[O_INFO] < MI && lane < n_me;                      // discard
+        else if (lane < 2 * H) ok = lane - H < n_me;                            // play
+        else if (lane < 2 * H + C) ok = st[O_INFO] > 0 && ((cmask >> (lane - 2 * H)) & 1u);      // reveal colour
+        else ok = st[O_INFO] > 0 && ((rmask >> (lane - 2 * H - C)) & 1u);                        // reveal rank
+        a.out_legal[(size_t)gi * g.A + lane] = ok ? 1.0f : 0.0f;
+      }
     }
     if (a.out_dump && lane == 0) {  // layout of oracle/hanabi_oracle.c:ohanabi_dump
       int32_t* o = a.out_dump + (size_t)gi * (5 + C + 2 * BPC + P * (1 + 5 * H));
