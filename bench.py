@@ -43,6 +43,7 @@ def parse_args():
     p.add_argument("--sims", type=int, default=50)
     p.add_argument("--stack", type=int, default=4)
     p.add_argument("--amp", default="torch_amp", choices=["torch_amp", "none"])
+    p.add_argument("--mdp", default="global", choices=["global", "local"], help="observation fed to the network")
     p.add_argument("--env-steps", type=int, default=200, help="env steps per timed env pass")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
@@ -259,17 +260,18 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
     cfg = SearchConfig(num_simulations=S, amp_type=args.amp)
     torch.manual_seed(0)
-    model = MuZeroNetFull(785 * args.stack, A).randomize_heads(seed=0).to(dev).eval()
+    obs_dim = 785 if args.mdp == "global" else 660
+    model = MuZeroNetFull(obs_dim * args.stack, A).randomize_heads(seed=0).to(dev).eval()
 
     # ---- synthetic roots: real Hanabi positions (reset + k random legal steps) -> initial inference ----
     env = HanabiVecEnv(N, "Hanabi-Full", np.arange(N) + rank * N, device=dev)
-    g, _, legal = env.reset_all()
+    g, loc, legal = env.reset_all()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     for _ in range(10):
         acts = torch.multinomial(legal, 1, generator=gen).view(-1).int()
-        g, _, legal, _, _, _ = env.step_all(acts, auto_reset=True, want_local=False)
+        g, loc, legal, _, _, _ = env.step_all(acts, auto_reset=True)
     env.check()
-    obs = g.repeat(1, args.stack)
+    obs = (g if args.mdp == "global" else loc).repeat(1, args.stack)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=args.amp == "torch_amp"):
         _, root_logits, root_hidden = model.initial_inference_device(obs)
     root_logits = root_logits.float().contiguous()
@@ -408,6 +410,25 @@ def run_ours(args):
     env.check()
     env_value = world * N * T / (float(env_ms.item()) * 1e-3)
     env_e2e = world * N * max(T // 4, 10) / (float(env_e2e_ms.item()) * 1e-3)
+    # ---- timed region 4 (informational): whole self-play moves, device-resident ----
+    from hanabizero_b200.selfplay import SelfPlayEngine
+    eng = SelfPlayEngine(N, "Hanabi-Full", model, cfg, seeds=np.arange(N) + 7 * N * (rank + 1), mdp=args.mdp,
+                         stack=args.stack, device=dev)
+    eng.reset()
+    for _ in range(3):
+        eng.step()
+    barrier()
+    e0.record()
+    n_moves = 5
+    for _ in range(n_moves):
+        eng.step()
+    e1.record()
+    barrier()
+    sp_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(sp_ms, op=dist.ReduceOp.MAX)
+    eng.env.check()
+    selfplay_moves = world * N * n_moves / (float(sp_ms.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant tree kernel (fused backprop+traverse+gather), timed live ----------
@@ -540,7 +561,7 @@ def run_ours(args):
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Hanabi-Full 2p global MDP, {N} trees/GPU x {S} simulations ({S - 1} executed, "
+            "config": {"workload": f"Hanabi-Full 2p {args.mdp} {'MDP' if args.mdp == 'global' else 'POMDP'}, {N} trees/GPU x {S} simulations ({S - 1} executed, "
                                    "as core/mcts.py:25-26), MuZeroNetFull random-init with re-drawn heads",
                        "trees_per_gpu": N, "trees_total": world * N, "actions": A, "simulations": S, "stack": args.stack,
                        "model_amp": args.amp, "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
@@ -555,6 +576,10 @@ def run_ours(args):
                             "d2h_bytes_per_step": 4 * N * (env.global_dim + A)},
                     "games_per_gpu": N, "steps_timed": T, "includes": "on-device random legal action pick (3 torch kernels) + "
                     "fused step/auto-reset/observe kernel", "roofline": env_roof},
+            "selfplay": {"metric": "selfplay_moves_per_sec", "value": selfplay_moves, "unit": "moves/s",
+                         "what": "frame stack -> representation+prediction -> Roots.prepare(Dirichlet) -> run_multi -> "
+                                 "select_action -> env step with auto-reset, all on the device (SelfPlayEngine.step)",
+                         "simulations_per_sec": selfplay_moves * (S - 1)},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

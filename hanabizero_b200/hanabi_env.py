@@ -90,7 +90,7 @@ class HanabiVecEnv:
         return g, l, a
 
     def step_all(self, actions, active=None, auto_reset=False, observe=True, out_global=None,
-                 out_local=None, out_legal=None, want_local=True):
+                 out_local=None, out_legal=None, want_local=True, want_global=True):
         """HanabiEnv.step for every (active) game in one launch.  actions: int32 CUDA tensor [N]
         (anything else is converted).  Returns (global_obs, local_obs, legal, reward, done, score).
         With auto_reset a finished game is re-dealt inside the same launch and the returned
@@ -107,7 +107,7 @@ class HanabiVecEnv:
             check(self._lib.hz_envs_step(self._h, self._stream(), ptr(actions), ptr(act),
                                          ptr(self.reward), ptr(self.done), ptr(self.score)))
             return None, None, None, self.reward, self.done, self.score
-        g = self.global_obs if out_global is None else out_global
+        g = (self.global_obs if out_global is None else out_global) if want_global else None
         l = (self.local_obs if out_local is None else out_local) if want_local else None
         a = self.legal if out_legal is None else out_legal
         check(self._lib.hz_envs_step_observe(

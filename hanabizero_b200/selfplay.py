@@ -112,16 +112,12 @@ class SelfPlayEngine:
         self.mcts.run_multi(roots, self.model, hidden)
         visits, values = roots.get_stats_tensors()
         actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
+        # env.step for every game; finished games are re-dealt in the same launch and the observation of the
+        # current player is written straight into the staging row that feeds the frame stack
         g, l = self._observe_into()
         _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=True, out_global=g, out_local=l,
-                                                         out_legal=self.legal, want_local=l is not None) \
-            if g is not None else self._step_local(actions)
+                                                         out_legal=self.legal, want_global=g is not None,
+                                                         want_local=l is not None)
         self._push(done)
         return dict(action=actions, reward=reward.clone(), done=done.clone(), score=score.clone(), visits=visits,
                     root_value=values, entropy=entropy)
-
-    def _step_local(self, actions):
-        e = self.env
-        check(e._lib.hz_envs_step_observe(e._h, e._stream(), ptr(actions), None, 1, ptr(e.reward), ptr(e.done),
-                                          ptr(e.score), None, 0, ptr(self._obs), self._obs.stride(0), ptr(self.legal)))
-        return None, None, None, e.reward, e.done, e.score
