@@ -88,6 +88,56 @@ __device__ __forceinline__ float warp_decode8(const Logits8& x, const float* __r
   return (r != r) ? 0.0f : r;
 }
 
+// Two rows at once (value and reward of one tree): the same arithmetic per row as warp_decode8, with the
+// two rows' shuffle reductions issued side by side so their latencies overlap.
+__device__ __forceinline__ void warp_decode8_pair(const Logits8& xa, const Logits8& xb, const float* __restrict__ support,
+                                                  int width, float delta, int lane, float& out_a, float& out_b) {
+  const int c0 = lane * 8;
+  float ma = xa.v[0], mb = xb.v[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) {
+    ma = fmaxf(ma, xa.v[k]);
+    mb = fmaxf(mb, xb.v[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ta = __shfl_xor_sync(HZ_FULL, ma, o), tb = __shfl_xor_sync(HZ_FULL, mb, o);
+    ma = fmaxf(ma, ta);
+    mb = fmaxf(mb, tb);
+  }
+  float sea = 0.0f, swa = 0.0f, seb = 0.0f, swb = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (c0 + k < width) {
+      const float sp = support[c0 + k];
+      const float ea = __expf(xa.v[k] - ma), eb = __expf(xb.v[k] - mb);
+      sea += ea;
+      swa += ea * sp;
+      seb += eb;
+      swb += eb * sp;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t0 = __shfl_xor_sync(HZ_FULL, sea, o), t1 = __shfl_xor_sync(HZ_FULL, swa, o);
+    const float t2 = __shfl_xor_sync(HZ_FULL, seb, o), t3 = __shfl_xor_sync(HZ_FULL, swb, o);
+    sea += t0;
+    swa += t1;
+    seb += t2;
+    swb += t3;
+  }
+  const float eps = 0.001f;
+  const float va = (swa / sea) / delta, vb = (swb / seb) / delta;
+  float ra = (sqrtf(1.0f + 4.0f * eps * (fabsf(va) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
+  float rb = (sqrtf(1.0f + 4.0f * eps * (fabsf(vb) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
+  ra = ra * ra - 1.0f;
+  rb = rb * rb - 1.0f;
+  ra = (va < 0.0f ? -ra : ra) * delta;
+  rb = (vb < 0.0f ? -rb : rb) * delta;
+  out_a = (ra != ra) ? 0.0f : ra;
+  out_b = (rb != rb) ? 0.0f : rb;
+}
+
 template <typename T>
 __device__ __forceinline__ bool decode_vec_ok(const T* x, int64_t ld) {
   return (ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
