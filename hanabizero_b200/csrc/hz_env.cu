@@ -98,13 +98,6 @@ __device__ __forceinline__ uint32_t mt_draw(uint32_t* mt, int& mti, MtWindow& wi
   return z;
 }
 
-__device__ __forceinline__ double shfl_double(double v, int src) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  lo = __shfl_sync(HZ_FULL, lo, src);
-  hi = __shfl_sync(HZ_FULL, hi, src);
-  return __hiloint2double(hi, lo);
-}
-
 __device__ __forceinline__ int player_to_deal(const uint8_t* st, int H) {  // hanabi_state.cc:157-164
   if (st[O_HLEN] < H) return 0;
   if (st[O_HLEN + 1] < H) return 1;

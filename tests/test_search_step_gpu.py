@@ -129,6 +129,7 @@ def _run(N, A, S, width, dtype, deep=False, seed=0):
     (129, 11, 40, 51, torch.float32),      # Hanabi-Small shapes, float pool
     (64, 20, 130, 201, torch.float16),     # capacity > 64: 8 q registers per lane
     (33, 20, 300, 201, torch.float32),     # capacity > 256: general back-propagation routine
+    (2048, 20, 200, 201, torch.float16),   # BASELINE configs[4] per-GPU shard: 16384 trees x 200 sims over 8 GPUs
 ])
 def test_search_step_equals_generic_calls(N, A, S, width, dtype):
     _run(N, A, S, width, dtype)
