@@ -143,6 +143,59 @@ def cpu_reference(trees, A, S, cores, reps=1, env_steps_per_core=20000):
                 wall_s=wall)
 
 
+def reference_with_model(trees, A, S):
+    """Informational: the loop of core/mcts.py:24-55 exactly as the reference runs it — its own cytree on the
+    host, the PyTorch network on the GPU, Python-list marshalling, host hidden-state gather, H2D of the batch
+    and D2H of the outputs EVERY simulation (one actor process).  Returns simulations/s or None."""
+    try:
+        import importlib.util
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        so = [f for f in os.listdir(os.path.join(ROOT, "oracle", "_ref")) if f.startswith("cytree.") and f.endswith(".so")]
+        if not so:
+            return None
+        spec = importlib.util.spec_from_file_location("cytree", os.path.join(ROOT, "oracle", "_ref", so[0]))
+        tree = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(tree)
+        from hanabizero_b200.model import MuZeroNetFull
+        torch.manual_seed(0)
+        model = MuZeroNetFull(785 * 4, A).randomize_heads(seed=0).cuda().eval()
+        rng = np.random.default_rng(0)
+        obs = torch.from_numpy((rng.random((trees, 785 * 4)) < 0.2).astype(np.float32)).cuda()
+        best = None
+        for rep in range(2):
+            with torch.no_grad():
+                with torch.autocast("cuda", dtype=torch.float16):
+                    out = model.initial_inference(obs)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                roots = tree.Roots(trees, A, S)
+                noises = [rng.dirichlet([0.3] * A).astype(np.float32).tolist() for _ in range(trees)]
+                roots.prepare(CONST["frac"], noises, out.reward, out.policy_logits.tolist(), [np.ones(A) for _ in range(trees)])
+                pool = [out.hidden_state]
+                mm = tree.MinMaxStatsList(trees)
+                mm.set_delta(CONST["delta"])
+                for x in range(1, S):
+                    results = tree.ResultsWrapper(trees)
+                    ix, iy, la = tree.multi_traverse(roots, CONST["pb_c_base"], CONST["pb_c_init"], CONST["discount"], mm, results)
+                    hs = torch.from_numpy(np.asarray([pool[a][b] for a, b in zip(ix, iy)])).to("cuda")
+                    la = torch.from_numpy(np.asarray(la)).to("cuda").unsqueeze(1).long()
+                    with torch.autocast("cuda", dtype=torch.float16):
+                        no = model.recurrent_inference(hs.float(), la)
+                    pol = no.policy_logits
+                    pol[np.isnan(pol)] = 0.0
+                    pool.append(no.hidden_state)
+                    tree.multi_back_propagate(x, CONST["discount"], no.reward.reshape(-1).tolist(),
+                                              no.value.reshape(-1).tolist(), pol.tolist(), mm, results)
+                roots.get_distributions(); roots.get_values()
+                dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return trees * (S - 1) / best
+    except Exception as e:  # informational only
+        return f"unavailable: {type(e).__name__}: {e}"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,6 +226,11 @@ def run_reference(args):
         "env": {"metric": "hanabi_env_steps_per_sec", "value": env, "unit": "steps/s", "kind": out["env_kind"],
                 "cores": out["cores"]},
         "gpu_launches": 0,
+        "reference_with_model_on_gpu": {
+            "value": reference_with_model(min(args.trees, 1024), A, S), "unit": "simulations/s",
+            "what": "informational: one reference actor, its own cytree on the host + the PyTorch network on cuda:0 with "
+                    "per-simulation H2D/D2H and list marshalling exactly as core/mcts.py:24-55 does, "
+                    f"{min(args.trees, 1024)} trees x {S - 1} simulations"},
     }
     print(json.dumps(line), flush=True)
 
