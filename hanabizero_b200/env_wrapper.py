@@ -1,17 +1,21 @@
-"""Drop-in for config/hanabi_control/env_wrapper.py:6-34 (HanabiControlWrapper) and the `Game`
-base it derives from (core/game.py:26-46): selects the global (MDP, 785/193 wide) or local
-(POMDP, 660/173 wide) observation and wraps every return value in numpy arrays."""
+"""Host-side view the reference's actors hold on one game: drop-in for
+config/hanabi_control/env_wrapper.py:6-34 (`HanabiControlWrapper`) and its base core/game.py:26-46 (`Game`).
+
+The wrapper only selects which observation the agent sees — the global / MDP one (own hand ‖ canonical
+encoding ‖ turn, 785 or 193 wide) or the local / POMDP one (660 / 173) — and hands every field back as a
+numpy array, as the reference does.  All game logic stays in the CUDA kernels behind `HanabiEnv`.
+"""
 import numpy as np
+
+_VIEWS = {"global": 0, "local": 1}   # index into (share_obs, obs) as returned by HanabiEnv
 
 
 class Game:
-    """core/game.py:26-46."""
+    """core/game.py:26-46: the minimal environment handle the self-play code passes around."""
 
     def __init__(self, env, action_space_size, discount, config=None):
-        self.env = env
-        self.action_space_size = action_space_size
-        self.discount = discount
-        self.config = config
+        self.env, self.action_space_size = env, action_space_size
+        self.discount, self.config = discount, config
 
     def legal_actions(self):
         raise NotImplementedError
@@ -31,24 +35,24 @@ class Game:
 
 class HanabiControlWrapper(Game):
     def __init__(self, env, discount, cvt_string=False, mdp="global"):
+        if mdp not in _VIEWS:   # the reference falls through and returns None for anything else
+            raise ValueError(f"mdp must be one of {sorted(_VIEWS)}, got {mdp!r}")
         super().__init__(env, env.num_moves(), discount)
-        self.cvt_string = cvt_string
-        if mdp not in ("global", "local"):
-            raise ValueError("mdp must be 'global' or 'local'")  # the reference silently returns None
-        self.mdp = mdp
+        self.cvt_string, self.mdp = cvt_string, mdp
+
+    def _view(self, pair):
+        return np.array(pair[_VIEWS[self.mdp]])
 
     def legal_actions(self):
         return list(range(self.action_space_size))
 
-    def step(self, action):
-        global_state, state, reward, done, info, legal_actions = self.env.step(action)
-        obs = global_state if self.mdp == "global" else state
-        return np.array(obs), np.array(reward), np.array(done), np.array(info), np.array(legal_actions)
-
     def reset(self, **kwargs):
-        global_state, state, legal_actions = self.env.reset()
-        obs = global_state if self.mdp == "global" else state
-        return np.array(obs), np.array(legal_actions)
+        *views, legal = self.env.reset()
+        return self._view(views), np.array(legal)
+
+    def step(self, action):
+        *views, reward, done, info, legal = self.env.step(action)
+        return (self._view(views),) + tuple(np.array(x) for x in (reward, done, info, legal))
 
     def close(self):
         pass
