@@ -145,7 +145,14 @@ class RecurrentPlan:
 
     # -- weights ---------------------------------------------------------------------------------------
     def _signature(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.net.parameters()) + list(self.net.buffers()))
+        """Version counters of every parameter / buffer: in-place updates (optimizer steps, load_state_dict,
+        BN statistics) bump tensor._version.  Walking the module costs ~200 us, reading the counters of a cached
+        tensor list ~12 us, so the list is re-enumerated only every 64th call (that is when a parameter that was
+        re-assigned rather than updated in place is noticed)."""
+        self._sig_calls = getattr(self, "_sig_calls", 0) + 1
+        if getattr(self, "_tensors", None) is None or self._sig_calls % 64 == 0:
+            self._tensors = list(self.net.parameters()) + list(self.net.buffers())
+        return tuple(t._version for t in self._tensors) + tuple(t.data_ptr() for t in self._tensors[:2])
 
     def _set(self, name, value):
         value = value.to(self.dtype).contiguous()
