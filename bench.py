@@ -604,15 +604,16 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        one = cpu_reference(min(N, 1024), A, S, 1, reps=1, env_steps_per_core=20000)
-        allc = cpu_reference(N, A, S, cores, reps=2, env_steps_per_core=20000)
+        one = cpu_reference(min(N, 1024), A, S, 1, reps=4, env_steps_per_core=100000)
+        allc = cpu_reference(N, A, S, cores, reps=6, env_steps_per_core=100000)
         cpu = {"value": allc["sims_per_s"], "unit": "simulations/s", "cores": allc["cores"], "kind": allc["kind"],
                "value_1core": one["sims_per_s"],
                "env_steps_per_s": allc["env_steps_per_s"], "env_steps_per_s_1core": one["env_steps_per_s"],
                "env_kind": allc["env_kind"],
-               "sample": (f"{N} Hanabi-Full trees x {S - 1} simulations x 2 over {allc['cores']} processes (and "
-                          f"{min(N, 1024)} trees on 1 core): reference cytree driven like core/mcts.py with pre-generated "
-                          "network outputs, no model time; env: 20000 steps/core of reference libhanabi in C++")}
+               "sample": (f"{N} Hanabi-Full trees x {S - 1} simulations x 6 over {allc['cores']} processes (and "
+                          f"{min(N, 1024)} trees x 4 on 1 core): reference cytree driven like core/mcts.py with pre-generated "
+                          "network outputs, no model time; env: 100000 steps/core of reference libhanabi in C++ "
+                          "(about 20 core-seconds in total)")}
 
     if rank == 0:
         line = {
