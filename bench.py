@@ -67,7 +67,8 @@ def _ref_tree_worker(args):
     Python-list marshalling, host hidden-state gather and .tolist() included, as the reference pays."""
     n, A, S, seed, reps = args
     import importlib.util
-    so = [f for f in os.listdir(os.path.join(ROOT, "oracle", "_ref")) if f.startswith("cytree.") and f.endswith(".so")]
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    so = [f for f in os.listdir(ref_dir) if f.startswith("cytree.") and f.endswith(".so")] if os.path.isdir(ref_dir) else []
     kind = "reference"
     if so:
         spec = importlib.util.spec_from_file_location("cytree", os.path.join(ROOT, "oracle", "_ref", so[0]))
@@ -152,7 +153,8 @@ def reference_with_model(trees, A, S):
         import torch
         if not torch.cuda.is_available():
             return None
-        so = [f for f in os.listdir(os.path.join(ROOT, "oracle", "_ref")) if f.startswith("cytree.") and f.endswith(".so")]
+        ref_dir = os.path.join(ROOT, "oracle", "_ref")
+        so = [f for f in os.listdir(ref_dir) if f.startswith("cytree.") and f.endswith(".so")] if os.path.isdir(ref_dir) else []
         if not so:
             return None
         spec = importlib.util.spec_from_file_location("cytree", os.path.join(ROOT, "oracle", "_ref", so[0]))
