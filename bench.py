@@ -429,12 +429,21 @@ def run_ours(args):
     acts_buf = torch.zeros(N, dtype=torch.int32, device=dev)
 
     def env_pass(steps, host):
+        """host: None = device-resident; "f32" / "u8" = scalar-API style (actions come from the host, the
+        observation and the legal mask go back to the host every step) with float32 or byte observations."""
         nonlocal legal
         for _ in range(steps):
-            if host:  # scalar-API style: actions come from the host, observations go back to the host
+            if host:
                 acts_buf.copy_(h_acts, non_blocking=True)
             else:
                 acts_buf.copy_(torch.argmax(legal * torch.rand_like(legal), dim=1))
+            if host == "u8":
+                env.step_all(acts_buf, auto_reset=True, want_local=False, out_global=g8, out_legal=legal8)
+                h_obs8.copy_(g8_store, non_blocking=True)
+                h_leg8.copy_(legal8, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                h_acts.copy_(torch.from_numpy(np.argmax(h_leg8.numpy() * host_rand, axis=1).astype(np.int32)))
+                continue
             gg, _, legal, r, d, s = env.step_all(acts_buf, auto_reset=True, want_local=False)
             if host:
                 h_obs.copy_(gg, non_blocking=True)
@@ -442,34 +451,44 @@ def run_ours(args):
                 torch.cuda.current_stream().synchronize()
                 h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
 
+    gpad = (env.global_dim + 15) // 16 * 16
+    g8_store = torch.zeros(N, gpad, dtype=torch.uint8, device=dev)     # 16-byte-multiple rows: word stores
+    g8, legal8 = g8_store[:, :env.global_dim], torch.zeros(N, A, dtype=torch.uint8, device=dev)
     h_obs = torch.empty(N, env.global_dim).pin_memory()
     h_leg = torch.empty(N, A).pin_memory()
+    h_obs8 = torch.empty(N, gpad, dtype=torch.uint8).pin_memory()
+    h_leg8 = torch.empty(N, A, dtype=torch.uint8).pin_memory()
     h_acts = torch.zeros(N, dtype=torch.int32).pin_memory()
     host_rand = rng.random((N, A)).astype(np.float32) + 0.01
-    h_leg.copy_(legal); torch.cuda.synchronize()
-    h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
-    env_pass(20, False)
-    barrier()
-    e0.record()
-    env_pass(T, False)
-    e1.record()
-    barrier()
-    env_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    h_leg.copy_(legal); torch.cuda.synchronize()
-    h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
-    env_pass(5, True)
-    barrier()
-    e0.record()
-    env_pass(max(T // 4, 10), True)
-    e1.record()
-    barrier()
-    env_e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(env_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(env_e2e_ms, op=dist.ReduceOp.MAX)
+
+    def host_pick():
+        h_leg.copy_(legal); torch.cuda.synchronize()
+        h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
+
+    def timed_env(steps, host, warm):
+        if host:
+            host_pick()
+        env_pass(warm, host)
+        barrier()
+        e0.record()
+        env_pass(steps, host)
+        e1.record()
+        barrier()
+        if host == "u8":       # the float legal mask of the device path is stale after byte steps
+            env.observe()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * N * steps / (float(t.item()) * 1e-3)
+
+    T_host = max(T // 4, 10)
+    env_value = timed_env(T, None, 20)
+    legal = env.legal
+    env_e2e_f32 = timed_env(T_host, "f32", 5)
+    legal = env.legal
+    env_e2e = timed_env(T_host, "u8", 5)
+    legal = env.legal
     env.check()
-    env_value = world * N * T / (float(env_ms.item()) * 1e-3)
-    env_e2e = world * N * max(T // 4, 10) / (float(env_e2e_ms.item()) * 1e-3)
     # ---- timed region 4 (informational): whole self-play moves, device-resident ----
     from hanabizero_b200.selfplay import SelfPlayEngine
     eng = SelfPlayEngine(N, "Hanabi-Full", model, cfg, seeds=np.arange(N) + 7 * N * (rank + 1), mdp=args.mdp,
@@ -634,7 +653,11 @@ def run_ours(args):
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "env": {"metric": "hanabi_env_steps_per_sec", "value": env_value, "unit": "steps/s",
                     "e2e": {"value": env_e2e, "unit": "steps/s", "h2d_bytes_per_step": 4 * N,
-                            "d2h_bytes_per_step": 4 * N * (env.global_dim + A)},
+                            "d2h_bytes_per_step": N * (gpad + A), "obs_dtype": "u8",
+                            "what": "actions from pinned host memory in, global observation + legal mask out as 0/1 "
+                                    "bytes (the encoder's own value type, hz_envs_step_observe_u8), host picks the next "
+                                    "action; one sync per step",
+                            "f32": {"value": env_e2e_f32, "d2h_bytes_per_step": 4 * N * (env.global_dim + A)}},
                     "games_per_gpu": N, "steps_timed": T, "includes": "on-device random legal action pick (3 torch kernels) + "
                     "fused step/auto-reset/observe kernel", "roofline": env_roof},
             "selfplay": {"metric": "selfplay_moves_per_sec", "value": selfplay_moves, "unit": "moves/s",

@@ -62,6 +62,8 @@ SIGNATURES = {
     "hz_envs_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hz_envs_observe": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "hz_envs_step_observe": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "hz_envs_observe_u8": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
+    "hz_envs_step_observe_u8": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "hz_envs_check": (_i, [_vp, _vp, _vp]),
     "hz_envs_dump": (_i, [_vp, _vp, _vp]),
 }

@@ -393,6 +393,23 @@ __device__ __forceinline__ void obs_segment(const uint8_t* st, int cur, uint32_t
   }
 }
 
+// bits [bit0, bit0 + n) of `words` (one spare word follows the last) as n bytes of 0/1; four bytes per lane
+// and store when the row is 4-byte aligned, so a warp store covers 128 contiguous bytes
+__device__ __forceinline__ void store_bits_u8(uint8_t* dst, const uint32_t* words, int bit0, int n, int lane) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+    const int n4 = n >> 2;
+    for (int g4 = lane; g4 < n4; g4 += HZ_WARP) {
+      const int b = bit0 + 4 * g4;
+      const uint32_t x = __funnelshift_r(words[b >> 5], words[(b >> 5) + 1], b & 31) & 15u;
+      reinterpret_cast<uint32_t*>(dst)[g4] = (x & 1u) | ((x & 2u) << 7) | ((x & 4u) << 14) | ((x & 8u) << 21);
+    }
+    const int j = 4 * n4 + lane;
+    if (j < n) dst[j] = (uint8_t)((words[(bit0 + j) >> 5] >> ((bit0 + j) & 31)) & 1u);
+  } else {
+    for (int j = lane; j < n; j += HZ_WARP) dst[j] = (uint8_t)((words[(bit0 + j) >> 5] >> ((bit0 + j) & 31)) & 1u);
+  }
+}
+
 struct EnvView {
   uint8_t* state;   // [N][128]
   uint32_t* mt;     // [N][624]
@@ -416,6 +433,11 @@ struct EnvArgs {
   int64_t ld_local;
   float* out_legal;
   int32_t* out_dump;
+  // byte-valued (0/1) observation outputs: the encoder's own value type (vector<int> of 0/1,
+  // canonical_encoders.cc:441-486) at a quarter of the float traffic; strides shared with the float rows
+  uint8_t* out_global8;
+  uint8_t* out_local8;
+  uint8_t* out_legal8;
 };
 
 template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
@@ -486,16 +508,22 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
     __syncwarp();
     float* og = a.out_global ? a.out_global + (size_t)gi * a.ld_global : nullptr;
     float* ol = a.out_local ? a.out_local + (size_t)gi * a.ld_local : nullptr;
+    if (og || ol) {
 #pragma unroll 5
-    for (int it = 0; it < (L::GLOBAL + 31) / 32; ++it) {
-      const int j = it * 32 + lane;
-      const float v = ((words[it] >> lane) & 1u) ? 1.0f : 0.0f;
-      if (j < L::GLOBAL) {
-        if (og) og[j] = v;
-        if (ol && j >= L::OWN) ol[j - L::OWN] = v;
+      for (int it = 0; it < (L::GLOBAL + 31) / 32; ++it) {
+        const int j = it * 32 + lane;
+        const float v = ((words[it] >> lane) & 1u) ? 1.0f : 0.0f;
+        if (j < L::GLOBAL) {
+          if (og) og[j] = v;
+          if (ol && j >= L::OWN) ol[j - L::OWN] = v;
+        }
       }
     }
-    if (a.out_legal) {
+    uint8_t* og8 = a.out_global8 ? a.out_global8 + (size_t)gi * a.ld_global : nullptr;
+    uint8_t* ol8 = a.out_local8 ? a.out_local8 + (size_t)gi * a.ld_local : nullptr;
+    if (og8) store_bits_u8(og8, words, 0, L::GLOBAL, lane);
+    if (ol8) store_bits_u8(ol8, words, L::OWN, L::GLOBAL - L::OWN, lane);
+    if (a.out_legal || a.out_legal8) {
       // LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all uids at once: lanes first agree on
       // which colours / ranks the partner's hand holds, then each lane tests its own move id
       const int other = (cur + 1) % P, n_me = st[O_HLEN + cur], n_ot = st[O_HLEN + other];
@@ -508,7 +536,8 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
         else if (lane < 2 * H) ok = lane - H < n_me;                            // play
         else if (lane < 2 * H + C) ok = st[O_INFO] > 0 && ((cmask >> (lane - 2 * H)) & 1u);      // reveal colour
         else ok = st[O_INFO] > 0 && ((rmask >> (lane - 2 * H - C)) & 1u);                        // reveal rank
-        a.out_legal[(size_t)gi * g.A + lane] = ok ? 1.0f : 0.0f;
+        if (a.out_legal) a.out_legal[(size_t)gi * g.A + lane] = ok ? 1.0f : 0.0f;
+        if (a.out_legal8) a.out_legal8[(size_t)gi * g.A + lane] = ok ? 1 : 0;
       }
     }
     if (a.out_dump && lane == 0) {  // layout of oracle/hanabi_oracle.c:ohanabi_dump
@@ -654,7 +683,7 @@ int hz_envs_reset(hz_envs* e, void* stream, const uint8_t* reset_mask) {
   return HZ_OK;
 }
 
-static int check_obs_args(const hz_envs* e, const float* og, int64_t ldg, const float* ol, int64_t ldl) {
+static int check_obs_args(const hz_envs* e, const void* og, int64_t ldg, const void* ol, int64_t ldl) {
   if ((og && ldg < e->g.own_len + e->g.enc_len + P) || (ol && ldl < e->g.enc_len + P)) {
     set_error("observation row stride smaller than the observation");
     return HZ_ERR_ARG;
@@ -698,6 +727,34 @@ int hz_envs_step_observe(hz_envs* e, void* stream, const int32_t* actions, const
   a.out_reward = out_reward; a.out_done = out_done; a.out_score = out_score;
   a.out_global = out_global; a.ld_global = ld_global;
   a.out_local = out_local; a.ld_local = ld_local; a.out_legal = out_legal;
+  return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
+}
+
+int hz_envs_observe_u8(hz_envs* e, void* stream, uint8_t* out_global, int64_t ld_global, uint8_t* out_local,
+                       int64_t ld_local, uint8_t* out_legal) {
+  if (!e) { set_error("hz_envs_observe_u8: NULL handle"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_observe_u8: reset first"); return HZ_ERR_STATE; }
+  if (int rc = check_obs_args(e, out_global, ld_global, out_local, ld_local)) return rc;
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.out_global8 = out_global; a.ld_global = ld_global;
+  a.out_local8 = out_local; a.ld_local = ld_local; a.out_legal8 = out_legal;
+  return launch_env<false, false, true>(e, (cudaStream_t)stream, a);
+}
+
+int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active,
+                            int auto_reset, int32_t* out_reward, uint8_t* out_done, int32_t* out_score,
+                            uint8_t* out_global, int64_t ld_global, uint8_t* out_local, int64_t ld_local,
+                            uint8_t* out_legal) {
+  if (!e || !actions) { set_error("hz_envs_step_observe_u8: NULL argument"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_step_observe_u8: reset first"); return HZ_ERR_STATE; }
+  if (int rc = check_obs_args(e, out_global, ld_global, out_local, ld_local)) return rc;
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.actions = actions; a.active = active; a.auto_reset = auto_reset;
+  a.out_reward = out_reward; a.out_done = out_done; a.out_score = out_score;
+  a.out_global8 = out_global; a.ld_global = ld_global;
+  a.out_local8 = out_local; a.ld_local = ld_local; a.out_legal8 = out_legal;
   return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
 }
 

@@ -26,7 +26,12 @@ class HanabiVecEnv:
     seeds[i], which persists across resets exactly like the reference's per-env HanabiGame object
     (rl_env.py:137,249)."""
 
-    def __init__(self, num_games, hanabi_name="Hanabi-Full", seeds=None, device=None):
+    def __init__(self, num_games, hanabi_name="Hanabi-Full", seeds=None, device=None, obs_dtype=torch.float32):
+        """obs_dtype: torch.float32 (what the network eats) or torch.uint8 (0/1 bytes: the encoder's own value
+        type at a quarter of the traffic; rows are padded to a 16-byte multiple so the kernel stores words)."""
+        if obs_dtype not in (torch.float32, torch.uint8):
+            raise ValueError("obs_dtype must be torch.float32 or torch.uint8")
+        self.obs_dtype = obs_dtype
         if hanabi_name not in PRESETS:
             raise ValueError("Unknown environment {}".format(hanabi_name))  # rl_env.py:133
         self.num_games = int(num_games)
@@ -51,9 +56,10 @@ class HanabiVecEnv:
         self.reward = torch.zeros(n, dtype=torch.int32, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.score = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.global_obs = torch.zeros(n, self.global_dim, dtype=torch.float32, device=dev)
-        self.local_obs = torch.zeros(n, self.local_dim, dtype=torch.float32, device=dev)
-        self.legal = torch.zeros(n, self.num_actions, dtype=torch.float32, device=dev)
+        pad = (lambda d: (d + 15) // 16 * 16) if obs_dtype == torch.uint8 else (lambda d: d)
+        self.global_obs = torch.zeros(n, pad(self.global_dim), dtype=obs_dtype, device=dev)[:, :self.global_dim]
+        self.local_obs = torch.zeros(n, pad(self.local_dim), dtype=obs_dtype, device=dev)[:, :self.local_dim]
+        self.legal = torch.zeros(n, self.num_actions, dtype=obs_dtype, device=dev)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -85,9 +91,19 @@ class HanabiVecEnv:
         g = self.global_obs if out_global is None else out_global
         l = self.local_obs if out_local is None else out_local
         a = self.legal if out_legal is None else out_legal
-        check(self._lib.hz_envs_observe(self._h, self._stream(), ptr(g), self._ld(g), ptr(l),
-                                        self._ld(l), ptr(a)))
+        fn = self._lib.hz_envs_observe_u8 if self._all_u8(g, l, a) else self._lib.hz_envs_observe
+        check(fn(self._h, self._stream(), ptr(g), self._ld(g), ptr(l), self._ld(l), ptr(a)))
         return g, l, a
+
+    @staticmethod
+    def _all_u8(*tensors):
+        """True if the output tensors are uint8, False if float32; mixed sets are rejected."""
+        kinds = {t.dtype for t in tensors if t is not None}
+        if kinds <= {torch.uint8}:
+            return bool(kinds)
+        if kinds <= {torch.float32}:
+            return False
+        raise TypeError(f"observation outputs must be all float32 or all uint8, got {sorted(map(str, kinds))}")
 
     def step_all(self, actions, active=None, auto_reset=False, observe=True, out_global=None,
                  out_local=None, out_legal=None, want_local=True, want_global=True):
@@ -110,9 +126,9 @@ class HanabiVecEnv:
         g = (self.global_obs if out_global is None else out_global) if want_global else None
         l = (self.local_obs if out_local is None else out_local) if want_local else None
         a = self.legal if out_legal is None else out_legal
-        check(self._lib.hz_envs_step_observe(
-            self._h, self._stream(), ptr(actions), ptr(act), 1 if auto_reset else 0, ptr(self.reward),
-            ptr(self.done), ptr(self.score), ptr(g), self._ld(g), ptr(l), self._ld(l), ptr(a)))
+        fn = self._lib.hz_envs_step_observe_u8 if self._all_u8(g, l, a) else self._lib.hz_envs_step_observe
+        check(fn(self._h, self._stream(), ptr(actions), ptr(act), 1 if auto_reset else 0, ptr(self.reward),
+                 ptr(self.done), ptr(self.score), ptr(g), self._ld(g), ptr(l), self._ld(l), ptr(a)))
         return g, l, a, self.reward, self.done, self.score
 
     def check(self):
@@ -233,7 +249,7 @@ class HanabiEnv:
 
     def __init__(self, args, device=None):
         seed = 0 if args["seed"] is None else args["seed"]  # rl_env.py:106-109
-        self._vec = HanabiVecEnv(1, args["hanabi_name"], [seed], device=device)
+        self._vec = HanabiVecEnv(1, args["hanabi_name"], [seed], device=device, obs_dtype=torch.uint8)
         v = self._vec
         self.game = _GameView(v)
         self.state = None

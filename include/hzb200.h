@@ -188,6 +188,16 @@ int hz_envs_step_observe(hz_envs* e, void* stream, const int32_t* actions, const
                          float* out_global, int64_t ld_global, float* out_local, int64_t ld_local,
                          float* out_legal);
 
+/* The same two calls with byte-valued outputs: every element is 0 or 1 as uint8 — the value type
+ * the reference encoder itself emits (std::vector<int> of 0/1, canonical_encoders.cc:441-486,
+ * serialised by pyhanabi.cc:855-895) at a quarter of the float32 traffic.  Row strides in bytes. */
+int hz_envs_observe_u8(hz_envs* e, void* stream, uint8_t* out_global, int64_t ld_global, uint8_t* out_local,
+                       int64_t ld_local, uint8_t* out_legal);
+int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active,
+                            int auto_reset, int32_t* out_reward, uint8_t* out_done, int32_t* out_score,
+                            uint8_t* out_global, int64_t ld_global, uint8_t* out_local, int64_t ld_local,
+                            uint8_t* out_legal);
+
 /* sync: returns HZ_ERR_ILLEGAL if any game saw an illegal action since the last check
  * (out_game = first offending game index), clearing the flag. */
 int hz_envs_check(hz_envs* e, void* stream, int32_t* out_game);

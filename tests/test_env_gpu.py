@@ -158,3 +158,43 @@ def test_scalar_dropin_api_and_errors():
     assert isinstance(o, np.ndarray) and o.shape == (173,) and lg2.shape == (11,)
     o, r, d, info, lg2 = w.step(int(np.flatnonzero(lg2)[0]))
     assert o.shape == (173,) and info.item()["score"] >= 0 and w.action_space_size == 11
+
+
+@pytest.mark.parametrize("name,preset", [("Hanabi-Full", 0), ("Hanabi-Small", 1)])
+def test_byte_observations_equal_float_observations(name, preset):
+    """hz_envs_*_u8: the 0/1 byte rows (aligned, padded rows take the 4-bytes-per-lane store; odd strides and
+    odd base addresses take the byte store) hold exactly the float rows' values, for reset, step and
+    auto-reset, and match the oracle on the first observation."""
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    from oracle import loader as L
+    N, T = 130, 90
+    seeds = np.arange(N) + 11
+    f_env = HanabiVecEnv(N, name, seeds)
+    b_env = HanabiVecEnv(N, name, seeds, obs_dtype=torch.uint8)
+    u_env = HanabiVecEnv(N, name, seeds, obs_dtype=torch.uint8)
+    gd, ld, A = f_env.global_dim, f_env.local_dim, f_env.num_actions
+    assert b_env.global_obs.stride(0) % 16 == 0 and b_env.global_obs.shape == (N, gd)
+    # unaligned targets for the third env: odd row stride and an odd base address
+    ug = torch.zeros(N * (gd + 3) + 1, dtype=torch.uint8, device="cuda")[1:].view(N, gd + 3)[:, :gd]
+    ul = torch.zeros(N * (ld + 1) + 3, dtype=torch.uint8, device="cuda")[3:].view(N, ld + 1)[:, :ld]
+    fg, fl, fa = f_env.reset_all()
+    bg, bl, ba = b_env.reset_all()
+    u_env.reset_all(observe=False)
+    _, _, ua = u_env.observe(out_global=ug, out_local=ul)
+    go, lo, lg = L.oracle_hanabi(preset, int(seeds[5])).reset()
+    assert (bg[5].cpu().numpy() == go).all() and (bl[5].cpu().numpy() == lo).all() and (ba[5].cpu().numpy() == lg).all()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(T):
+        for g8, l8, a8 in ((bg, bl, ba), (ug, ul, ua)):
+            assert g8.dtype == torch.uint8 and torch.equal(g8.float(), fg), t
+            assert torch.equal(l8.float(), fl) and torch.equal(a8.float(), fa), t
+        acts = torch.multinomial(fa, 1, generator=gen).view(-1).int()
+        fg, fl, fa, fr, fd, fs = f_env.step_all(acts, auto_reset=True)
+        bg, bl, ba, br, bd, bs = b_env.step_all(acts, auto_reset=True)
+        _, _, ua, ur, ud, us = u_env.step_all(acts, auto_reset=True, out_global=ug, out_local=ul)
+        assert torch.equal(fr, br) and torch.equal(fd, bd) and torch.equal(fs, bs)
+        assert torch.equal(fr, ur) and torch.equal(fd, ud) and torch.equal(fs, us)
+    with pytest.raises(TypeError):
+        f_env.observe(out_global=ug)     # float legal/local with a byte global row
+    for e in (f_env, b_env, u_env):
+        e.check()
