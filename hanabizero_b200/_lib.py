@@ -55,6 +55,10 @@ SIGNATURES = {
     "hz_bias_act": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i]),
     "hz_select_action": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "hz_stack_push": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i]),
+    "hz_traj_begin": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "hz_traj_append": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hz_traj_pack": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hz_visit_policy": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "hz_envs_create": (_i, [C.POINTER(_vp), _i, _i, _i, _vp]),
     "hz_envs_destroy": (_i, [_vp]),
     "hz_envs_dims": (_i, [_vp, _vp]),
@@ -79,6 +83,13 @@ class SearchIO(C.Structure):
                 ("ld_batch", _i64), ("onehot_cols", C.c_int32), ("out_ix", _vp), ("out_action", _vp),
                 ("minmax", _vp), ("value_delta_max", _f), ("discount", _f), ("pb_c_base", C.c_int32),
                 ("pb_c_init", _f)]
+
+
+class TrajView(C.Structure):
+    """struct hz_traj_view (include/hzb200.h)."""
+    _fields_ = [("obs", _vp), ("legal", _vp), ("action", _vp), ("reward", _vp), ("visits", _vp), ("root_value", _vp),
+                ("len", _vp), ("bank", _vp), ("finished", _vp), ("overflow", _vp), ("num", C.c_int32),
+                ("obs_dim", C.c_int32), ("actions", C.c_int32), ("stack", C.c_int32), ("max_len", C.c_int32), ("banks", C.c_int32)]
 
 
 class GemmStep(C.Structure):

@@ -61,7 +61,10 @@ def select_action(visit_counts, temperature=1, deterministic=True, legal_actions
 class SelfPlayEngine:
     """N Hanabi games + N trees advanced one move per `step()` entirely on one GPU."""
 
-    def __init__(self, num_games, hanabi_name, model, config, seeds=None, mdp="global", stack=4, device=None):
+    def __init__(self, num_games, hanabi_name, model, config, seeds=None, mdp="global", stack=4, device=None,
+                 record=False, max_episode_len=128, record_banks=2):
+        """record: keep every game's trajectory on the device (hanabizero_b200.trajectory, SURVEY §8f N3);
+        finished episodes are fetched with `self.recorder.flush()`."""
         self.env = HanabiVecEnv(num_games, hanabi_name, seeds, device=device)
         self.dev, self.n, self.stack, self.mdp = self.env.device, num_games, int(stack), mdp
         self.model, self.config, self.mcts = model, config, MCTS(config)
@@ -72,12 +75,24 @@ class SelfPlayEngine:
         self._obs = torch.zeros(num_games, self.obs_dim, device=self.dev)
         self._all_done = torch.ones(num_games, dtype=torch.uint8, device=self.dev)
         alpha = float(getattr(config, "root_dirichlet_alpha", 0.3))
+        self.recorder = None
+        if record:
+            from .trajectory import TrajectoryRecorder
+            self.recorder = TrajectoryRecorder(num_games, self.obs_dim, self.env.num_actions, self.stack,
+                                               max_episode_len, device=self.dev, banks=record_banks)
         self._gamma = torch.distributions.Gamma(torch.full((num_games, self.env.num_actions), alpha, device=self.dev),
                                                 torch.ones((), device=self.dev))
 
     def _observe_into(self):
         g, l = (self._obs, None) if self.mdp == "global" else (None, self._obs)
         return g, l
+
+    def _observe(self):
+        """The current player's observation (the view this engine feeds the network) and legal mask of every game."""
+        g, l = self._observe_into()
+        check(self.lib.hz_envs_observe(self.env._h, torch.cuda.current_stream(self.dev).cuda_stream, ptr(g),
+                                       0 if g is None else g.stride(0), ptr(l), 0 if l is None else l.stride(0),
+                                       ptr(self.legal)))
 
     def _push(self, done):
         check(self.lib.hz_stack_push(torch.cuda.current_stream(self.dev).cuda_stream, ptr(self.frames), ptr(self._obs),
@@ -86,11 +101,10 @@ class SelfPlayEngine:
     def reset(self):
         """env.reset() for every game; the first observation fills the whole stack (selfplay_worker.py:137)."""
         self.env.reset_all(observe=False)
-        g, l = self._observe_into()
-        check(self.lib.hz_envs_observe(self.env._h, torch.cuda.current_stream(self.dev).cuda_stream, ptr(g),
-                                       0 if g is None else g.stride(0), ptr(l), 0 if l is None else l.stride(0),
-                                       ptr(self.legal)))
+        self._observe()
         self._push(self._all_done)
+        if self.recorder is not None:
+            self.recorder.begin(self._obs, self.legal)
         return self.frames.view(self.n, -1), self.legal
 
     @torch.no_grad()
@@ -115,9 +129,23 @@ class SelfPlayEngine:
         # env.step for every game; finished games are re-dealt in the same launch and the observation of the
         # current player is written straight into the staging row that feeds the frame stack
         g, l = self._observe_into()
-        _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=True, out_global=g, out_local=l,
+        if self.recorder is None:
+            _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=True, out_global=g, out_local=l,
+                                                             out_legal=self.legal, want_global=g is not None,
+                                                             want_local=l is not None)
+            self._push(done)
+            return dict(action=actions, reward=reward.clone(), done=done.clone(), score=score.clone(), visits=visits,
+                        root_value=values, entropy=entropy)
+        # recording: the terminal observation belongs to the finished trajectory (GameHistory.append, game.py:143),
+        # so the step does not re-deal; finished games are reset by a masked launch after the append
+        _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=False, out_global=g, out_local=l,
                                                          out_legal=self.legal, want_global=g is not None,
                                                          want_local=l is not None)
-        self._push(done)
-        return dict(action=actions, reward=reward.clone(), done=done.clone(), score=score.clone(), visits=visits,
-                    root_value=values, entropy=entropy)
+        out = dict(action=actions, reward=reward.clone(), done=done.clone(), score=score.clone(), visits=visits,
+                   root_value=values, entropy=entropy, obs=self._obs.clone(), legal=self.legal.clone())
+        self.recorder.append(actions, self._obs, self.legal, reward, visits, values, done)
+        self.env.reset_all(mask=out["done"], observe=False)
+        self._observe()
+        self._push(out["done"])
+        self.recorder.begin(self._obs, self.legal, mask=out["done"])
+        return out

@@ -239,6 +239,52 @@ int hz_select_action(void* stream, int32_t* visits, const float* legal, const fl
 int hz_stack_push(void* stream, float* stack, const float* obs, int64_t ld_obs, const uint8_t* done, int num,
                   int stack_depth, int dim);
 
+/* Trajectory record of N self-play games in HBM: GameHistory.init /
+ * store_search_stats / append / game_over (/root/reference/core/game.py:73-93,143-148,176-204) for a
+ * whole batch.  The caller owns the buffers (device memory, zero-initialised) and passes this view.
+ * `banks` >= 2 banks per game (B below), used round-robin: an episode closed by done[i] waits in its bank for
+ * hz_traj_pack while the game's next episodes are recorded into the following banks.  Observations are 0/1
+ * valued and kept as bytes. */
+typedef struct hz_traj_view {
+  uint8_t* obs;        /* [N][B][stack + max_len][obs_dim]: `stack` copies of the first frame, then one per move */
+  uint8_t* legal;      /* [N][B][max_len + 1][actions]: legal mask before move t (row 0 from begin) */
+  int32_t* action;     /* [N][B][max_len] */
+  int32_t* reward;     /* [N][B][max_len] raw env rewards (the turn-reward reshaping of
+                          selfplay_worker.py:29-39 is applied when the episode is handed over) */
+  int32_t* visits;     /* [N][B][max_len][actions] root child visit counts */
+  float* root_value;   /* [N][B][max_len] */
+  int32_t* len;        /* [N][B] moves recorded in each bank */
+  uint8_t* bank;       /* [N] bank currently written */
+  uint8_t* finished;   /* [N][B] 1 = complete episode awaiting hz_traj_pack */
+  int32_t* overflow;   /* [1] sticky: 1 + first game that ran out of room (episode longer than max_len,
+                          or every bank full because the host did not pack in time) */
+  int32_t num, obs_dim, actions, stack, max_len, banks;
+} hz_traj_view;
+/* GameHistory.init for the games with mask[i] != 0 (dev uint8[N], NULL = all): the first observation
+ * (dev float[N][ld_obs]) fills the `stack` leading frames, the first legal mask (dev float[N][actions])
+ * row 0. */
+int hz_traj_begin(void* stream, const hz_traj_view* v, const float* obs, int64_t ld_obs, const float* legal,
+                  const uint8_t* mask);
+/* One self-play move of every game with active[i] != 0 (NULL = all): store_search_stats(visits, root_value)
+ * + append(action, obs, reward, legal); done[i] != 0 closes the episode (game_over) and moves on to the next bank —
+ * call hz_traj_begin with mask = done afterwards, once the env has been reset.  All pointers dev. */
+int hz_traj_append(void* stream, const hz_traj_view* v, const int32_t* actions, const float* obs, int64_t ld_obs,
+                   const float* legal, const int32_t* reward, const int32_t* visits, const float* root_values,
+                   const uint8_t* done, const uint8_t* active);
+/* Hand over finished episodes: episode e = (ep_game[e], ep_bank[e]) (dev int32) with T_e moves is copied to
+ * rows [step_off[e], step_off[e] + T_e) of out_action/out_reward/out_root/out_visits, to rows
+ * [step_off[e] + e*stack, +stack + T_e) of out_obs and [step_off[e] + e, +T_e + 1) of out_legal (dev
+ * int64 step_off = exclusive prefix sum of the T_e); the bank is freed. */
+int hz_traj_pack(void* stream, const hz_traj_view* v, int num_episodes, const int32_t* ep_game, const int32_t* ep_bank,
+                 const int64_t* step_off, uint8_t* out_obs, uint8_t* out_legal, int32_t* out_action,
+                 int32_t* out_reward, int32_t* out_visits, float* out_root);
+/* Policy targets from visit counts (store_search_stats, game.py:194-197; the reanalyze caller,
+ * /root/reference/core/reanalyze_worker.py:352-367): out[i][a] = visits[i][a] / sum_a visits[i]
+ * as a correctly rounded double quotient (Python's int / int), rows with mask[i] == 0 (dev uint8[N], NULL = keep
+ * all) all zero.  out64 double[N][A] and/or out32 float[N][A] (dev). */
+int hz_visit_policy(void* stream, const int32_t* visits, const uint8_t* mask, int num, int num_actions, double* out64,
+                    float* out32);
+
 /* A fixed chain of nn.Linear-shaped GEMMs executed with cuBLASLt, one launch each:
  *   D[m][n] = act( A[m][k] . W[n][k]^T + bias[n] + C[m][n] ),  all row-major, strided batches allowed.
  * Pointers are captured at creation (static buffers: the chain is CUDA-graph friendly). */
