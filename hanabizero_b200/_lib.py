@@ -44,6 +44,7 @@ SIGNATURES = {
     "hz_gemm_plan_create": (_i, [C.POINTER(_vp), _i, _i, _vp, _i]),
     "hz_gemm_plan_destroy": (_i, [_vp]),
     "hz_gemm_plan_steps": (_i, [_vp]),
+    "hz_gemm_plan_fused": (_i, [_vp]),
     "hz_gemm_launch_count": (_i64, []),
     "hz_gemm_plan_run": (_i, [_vp, _vp, _i, _i]),
     "hz_trees_set_progress": (_i, [_vp, _i]),

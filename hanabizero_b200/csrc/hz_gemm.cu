@@ -15,6 +15,7 @@
 
 #include <vector>
 
+#include "hz_chain.h"
 #include "hz_common.cuh"
 
 namespace hz {
@@ -50,6 +51,7 @@ struct hz_gemm_plan {
   size_t ws_bytes = 0;
   bool autotune = false;
   std::vector<LtStep> steps;
+  hz::ChainExec* fused = nullptr;   // persistent one-launch executor (hz_chain.cu), fp16 plans
 };
 
 #define HZ_LT(call)                                                         \
@@ -198,6 +200,12 @@ int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz
       return rc;
     }
   }
+  if (chain_supported(steps, n_steps, elem_bytes, nullptr)) {
+    if (int rc = chain_create(&p->fused, device, steps, n_steps)) {
+      hz_gemm_plan_destroy(p);
+      return rc;
+    }
+  }
   *out = p;
   return HZ_OK;
 }
@@ -205,6 +213,7 @@ int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz
 int hz_gemm_plan_destroy(hz_gemm_plan* p) {
   if (!p) return HZ_OK;
   DeviceGuard dg(p->device);
+  chain_destroy(p->fused);
   for (auto& st : p->steps) free_step(st);
   if (p->workspace) cudaFree(p->workspace);
   if (p->lt) cublasLtDestroy(p->lt);
@@ -216,12 +225,20 @@ int64_t hz_gemm_launch_count(void) { return g_gemm_launches.load(); }
 
 int hz_gemm_plan_steps(const hz_gemm_plan* p) { return p ? (int)p->steps.size() : 0; }
 
+int hz_gemm_plan_fused(const hz_gemm_plan* p) { return p && p->fused ? chain_grid(p->fused) : 0; }
+
+// debug (not in include/hzb200.h): per-CTA, per-step globaltimer stamps of the last fused run (HZ_CHAIN_TRACE=1)
+int hz_debug_chain_trace(const hz_gemm_plan* p, unsigned long long* out, int64_t count) {
+  return p ? chain_trace(p->fused, out, (size_t)count) : 0;
+}
+
 int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count) {
   if (!p || first < 0 || count < 0 || first + count > (int)p->steps.size()) {
     set_error("hz_gemm_plan_run: bad argument");
     return HZ_ERR_ARG;
   }
   DeviceGuard dg(p->device);
+  if (p->fused && first == 0 && count == (int)p->steps.size()) return chain_run(p->fused, (cudaStream_t)stream);
   const float alpha = 1.0f;
   for (int i = first; i < first + count; ++i) {
     LtStep& st = p->steps[i];

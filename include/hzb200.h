@@ -300,6 +300,10 @@ typedef struct hz_gemm_plan hz_gemm_plan;
 int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz_gemm_step* steps, int n_steps); /* sync */
 int hz_gemm_plan_destroy(hz_gemm_plan* p);                                                                     /* sync */
 int hz_gemm_plan_steps(const hz_gemm_plan* p);
+/* > 0 if a whole-plan run (first = 0, count = all) executes as ONE persistent tcgen05/TMA kernel of this library
+ * (fp16 plans; value = its grid size) instead of one cuBLASLt launch per step; 0 otherwise.  HZ_FUSED_CHAIN=0 in the
+ * environment keeps every plan on cuBLASLt. */
+int hz_gemm_plan_fused(const hz_gemm_plan* p);
 /* cuBLASLt launches issued through hz_gemm_plan_run in this process (library GEMMs, counted apart from
  * hz_launch_count, which counts this library's own kernels) */
 int64_t hz_gemm_launch_count(void);

@@ -1,0 +1,124 @@
+"""GPU: the persistent fused GEMM-chain executor (hz_chain.cu: TMA + tcgen05, one launch per recurrent_inference)
+against a float32 PyTorch evaluation of the same steps and against the cuBLASLt executor of the same plan.
+Floating point: fp16 storage, fp32 accumulation on both sides; tolerance 2e-3 relative to the row scale
+(accumulation order differs between the executors, every intermediate is rounded to fp16)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-3
+
+
+def _close(got, want, what):
+    got, want = got.float(), want.float()
+    scale = want.abs().amax(dim=-1, keepdim=True).clamp_min(1.0)
+    err = ((got - want).abs() / scale).max().item()
+    assert err <= RTOL, f"{what}: max scaled error {err:.3e}"
+
+
+def _make_plan(steps):
+    from hanabizero_b200 import _lib
+    lib = _lib.load()
+    arr = (_lib.GemmStep * len(steps))(*steps)
+    h = C.c_void_p()
+    _lib.check(lib.hz_gemm_plan_create(C.byref(h), torch.cuda.current_device(), 2, arr, len(steps)))
+    return lib, h
+
+
+def _step(a, w, bias, d, c=None, relu=True, batch=1, sa=0, sw=0, sb=0, sc=0, sd=0, m=None, n=None, k=None):
+    from hanabizero_b200 import _lib
+    s = _lib.GemmStep()
+    s.a, s.lda, s.stride_a = a.data_ptr(), a.stride(-2), sa
+    s.w, s.ldw, s.stride_w = w.data_ptr(), w.stride(-2), sw
+    s.bias, s.stride_bias = (0 if bias is None else bias.data_ptr()), sb
+    s.c, s.ldc, s.stride_c = (0 if c is None else c.data_ptr()), (0 if c is None else c.stride(-2)), sc
+    s.d, s.ldd, s.stride_d = d.data_ptr(), d.stride(-2), sd
+    s.m, s.n, s.k, s.batch, s.relu = m, n, k, batch, 1 if relu else 0
+    return s
+
+
+@pytest.mark.parametrize("m", [1, 96, 128, 300, 4096])
+def test_fused_chain_matches_float32_reference(m):
+    """A 4-step synthetic plan that exercises: K not a multiple of 64 (zero-filled tail block), a residual input with
+    a wider row stride, a strided batch of 3, a step without bias / ReLU, n = 208 (one 208-wide tile), row tails."""
+    from hanabizero_b200 import _lib
+    torch.manual_seed(m)
+    dev, h = "cuda", torch.float16
+    r = lambda *s: (torch.randn(*s, device=dev) * 0.25).to(h)
+    x0 = r(m, 544)
+    w1, b1, y1 = r(512, 544), r(512), torch.zeros(m, 512, device=dev, dtype=h)
+    w2, b2, y2 = r(768, 512), r(768), torch.zeros(m, 768, device=dev, dtype=h)
+    w3, b3, y3 = r(3, 256, 256), r(3, 256), torch.zeros(3, m, 256, device=dev, dtype=h)
+    w4, y4 = r(3, 208, 256), torch.zeros(3, m, 208, device=dev, dtype=h)
+    steps = [
+        _step(x0, w1, b1, y1, c=x0, m=m, n=512, k=544),
+        _step(y1, w2, b2, y2, m=m, n=768, k=512),
+        _step(y2, w3, b3, y3, batch=3, sa=256, sw=256 * 256, sb=256, sd=m * 256, m=m, n=256, k=256),
+        _step(y3, w4, None, y4, relu=False, batch=3, sa=m * 256, sw=208 * 256, sd=m * 208, m=m, n=208, k=256),
+    ]
+    lib, plan = _make_plan(steps)
+    assert lib.hz_gemm_plan_fused(plan) > 0, "the fp16 plan must run on the fused executor"
+    st = torch.cuda.current_stream().cuda_stream
+    before = _lib.launch_count()
+    _lib.check(lib.hz_gemm_plan_run(plan, st, 0, 4))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == before + 1          # ONE launch of this library's own kernel
+    got = [t.clone() for t in (y1, y2, y3, y4)]
+    f = lambda t: t.float()
+    e1 = torch.relu(f(x0) @ f(w1).T + f(b1) + f(x0)[:, :512]).to(h)
+    e2 = torch.relu(f(e1) @ f(w2).T + f(b2)).to(h)
+    e3 = torch.stack([torch.relu(f(e2[:, 256 * i:256 * i + 256]) @ f(w3[i]).T + f(b3[i])) for i in range(3)]).to(h)
+    e4 = torch.stack([f(e3[i]) @ f(w4[i]).T for i in range(3)]).to(h)
+    for g, e, name in zip(got, (e1, e2, e3, e4), ("step1", "step2", "step3", "step4")):
+        _close(g, e, name)
+    # the cuBLASLt executor of the same plan (partial ranges never take the fused path)
+    for t in (y1, y2, y3, y4):
+        t.zero_()
+    _lib.check(lib.hz_gemm_plan_run(plan, st, 0, 2))
+    _lib.check(lib.hz_gemm_plan_run(plan, st, 2, 2))
+    torch.cuda.synchronize()
+    for g, t, name in zip(got, (y1, y2, y3, y4), ("step1", "step2", "step3", "step4")):
+        _close(g, t, name + " vs cuBLASLt")
+    # repeated launches (the grid-barrier counters restore themselves) give identical bits
+    for _ in range(3):
+        _lib.check(lib.hz_gemm_plan_run(plan, st, 0, 4))
+    torch.cuda.synchronize()
+    for g, t in zip(got, (y1, y2, y3, y4)):
+        assert torch.equal(g, t)
+    _lib.check(lib.hz_gemm_plan_destroy(plan))
+
+
+@pytest.mark.parametrize("small", [False, True])
+@pytest.mark.parametrize("n", [96, 4096])
+def test_fused_chain_runs_the_recurrent_plan(small, n):
+    """The production plan (hanabizero_b200/plan.py) through the fused executor equals its cuBLASLt execution and
+    the PyTorch module within fp16 tolerance."""
+    from hanabizero_b200 import _lib
+    from hanabizero_b200.model import MuZeroNet, MuZeroNetFull
+    torch.manual_seed(1)
+    model = (MuZeroNet(193, 11) if small else MuZeroNetFull(785, 20)).randomize_heads().cuda().eval()
+    plan = model.recurrent_plan(torch.float16)
+    ch = plan.chain(n)
+    lib = _lib.load()
+    assert lib.hz_gemm_plan_fused(ch._h) > 0
+    hidden = (torch.randn(n, plan.F, device="cuda") * 0.5).half()
+    action = torch.randint(0, plan.A, (n, 1), device="cuda")
+    state = torch.empty(n, plan.F, device="cuda", dtype=torch.float16)
+    v, r, lg = plan.run(hidden, action, state)                       # fused (whole-plan run)
+    fused = [t.clone() for t in (ch.state, ch.out)]
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hz_gemm_plan_run(ch._h, st, 0, 1))
+    _lib.check(lib.hz_gemm_plan_run(ch._h, st, 1, ch.n_steps - 1))   # cuBLASLt
+    torch.cuda.synchronize()
+    _close(fused[0], ch.state, "next state vs cuBLASLt")
+    _close(fused[1][:, :, :plan.n_support], ch.out[:, :, :plan.n_support], "head logits vs cuBLASLt")
+    with torch.no_grad():
+        mv, mr, mlg, mstate = model.recurrent_inference_device(hidden.float(), action)
+    _close(state, mstate, "next state vs module")
+    _close(lg, mlg, "policy logits vs module")
+    np.testing.assert_allclose(v.cpu().numpy(), mv.cpu().numpy(), rtol=2e-2, atol=2e-2)
+    np.testing.assert_allclose(r.cpu().numpy(), mr.cpu().numpy(), rtol=2e-2, atol=2e-2)
