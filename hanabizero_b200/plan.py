@@ -138,7 +138,7 @@ class RecurrentPlan:
         self.n_support = net._value_support.numel()
         if net._reward_support.numel() != self.n_support:
             raise ValueError("value and reward supports must have the same size")
-        self.P3 = _round_up(self.n_support, 8)
+        self.P3 = _round_up(self.n_support, 16)   # 16: one tcgen05 column tile (hz_chain.cu)
         self.support = net._value_support.detach().float().contiguous()
         self._sig, self._w, self._chains = None, {}, {}
         self.refresh(force=True)

@@ -8,6 +8,11 @@ import numpy as np
 import pytest
 import torch
 
+import os
+
+# the fused executor is experimental and opt-in (it does not beat cuBLASLt yet: profiles/README.md); the tests opt in
+os.environ["HZ_FUSED_CHAIN"] = "1"
+
 pytestmark = pytest.mark.gpu
 
 RTOL = 2e-3
@@ -61,7 +66,7 @@ def test_fused_chain_matches_float32_reference(m):
         _step(y3, w4, None, y4, relu=False, batch=3, sa=m * 256, sw=208 * 256, sd=m * 208, m=m, n=208, k=256),
     ]
     lib, plan = _make_plan(steps)
-    assert lib.hz_gemm_plan_fused(plan) > 0, "the fp16 plan must run on the fused executor"
+    assert lib.hz_gemm_plan_fused(plan) > 0, "HZ_FUSED_CHAIN=1: the fp16 plan must run on the fused executor"
     st = torch.cuda.current_stream().cuda_stream
     before = _lib.launch_count()
     _lib.check(lib.hz_gemm_plan_run(plan, st, 0, 4))
