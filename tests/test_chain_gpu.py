@@ -8,12 +8,14 @@ import numpy as np
 import pytest
 import torch
 
-import os
-
-# the fused executor is experimental and opt-in (it does not beat cuBLASLt yet: profiles/README.md); the tests opt in
-os.environ["HZ_FUSED_CHAIN"] = "1"
-
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _opt_in(monkeypatch):
+    """The fused executor is experimental and opt-in (it does not beat cuBLASLt yet: profiles/README.md); plans
+    created inside these tests opt in, every other test keeps the production default."""
+    monkeypatch.setenv("HZ_FUSED_CHAIN", "1")
 
 RTOL = 2e-3
 
@@ -106,7 +108,7 @@ def test_fused_chain_runs_the_recurrent_plan(small, n):
     from hanabizero_b200.model import MuZeroNet, MuZeroNetFull
     torch.manual_seed(1)
     model = (MuZeroNet(193, 11) if small else MuZeroNetFull(785, 20)).randomize_heads().cuda().eval()
-    plan = model.recurrent_plan(torch.float16)
+    plan = model.recurrent_plan(torch.float16)      # a fresh model: its plan (and chains) are built under the opt-in
     ch = plan.chain(n)
     lib = _lib.load()
     assert lib.hz_gemm_plan_fused(ch._h) > 0
