@@ -61,7 +61,7 @@ class _Workspace:
 
 
 class MCTS(object):
-    max_cached_workspaces = 4
+    max_cached_workspaces = 8
 
     def __init__(self, config, use_plan=True):
         self.config = config
@@ -219,3 +219,81 @@ class MCTS(object):
 
 def _flat(x):
     return x.reshape(-1) if isinstance(x, torch.Tensor) else np.asarray(x).reshape(-1)
+
+
+class SearchPipeline:
+    """Host-fed searches, double-buffered: while search i runs on the compute stream, the inputs of search i+1 are
+    copied in from pinned host memory on a copy stream and the root statistics of search i-1 are copied out.
+    Each slot owns its tree batch (and therefore its captured search graph) and its device staging buffers, so
+    consecutive searches never share memory; `depth` searches can be in flight.
+
+        pipe = SearchPipeline(MCTS(cfg), model, num_roots, num_actions)
+        t = pipe.submit(fraction, noises, rewards, logits, legal, hidden_roots, out_visits, out_values)   # returns at once
+        ...
+        pipe.wait(t)          # out_visits / out_values (pinned host tensors) now hold the result of that search
+
+    Inputs are what Roots.prepare + MCTS.run_multi take (core/selfplay_worker.py:276-283), as pinned host tensors
+    (pageable memory works but serialises the copies); `noises=None` selects prepare_no_noise."""
+
+    def __init__(self, mcts, model, num_roots, num_actions, depth=2, device=None):
+        self.mcts, self.model = mcts, model
+        self.n, self.a, self.depth = int(num_roots), int(num_actions), int(depth)
+        self.device = next(model.parameters()).device if device is None else torch.device(device)
+        dev, sims = self.device, int(mcts.config.num_simulations)
+        self.compute = torch.cuda.current_stream(dev)
+        self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append(dict(
+                roots=cytree.Roots(self.n, self.a, sims, device=dev),
+                noise=torch.empty(self.n, self.a, device=dev), reward=torch.empty(self.n, device=dev),
+                logits=torch.empty(self.n, self.a, device=dev), legal=torch.empty(self.n, self.a, dtype=torch.int32, device=dev),
+                hidden=None, visits=torch.empty(self.n, self.a, dtype=torch.int32, device=dev),
+                values=torch.empty(self.n, device=dev),
+                ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False))
+        self._next = 0
+
+    def submit(self, fraction, noises, rewards, logits, legal, hidden_roots, out_visits, out_values):
+        i = self._next
+        self._next = (i + 1) % self.depth
+        s = self.slots[i]
+        if s["busy"]:
+            s["ev_out"].synchronize()          # the slot's previous search has been read out
+        s["busy"] = True
+        hidden_roots = torch.as_tensor(hidden_roots)
+        if s["hidden"] is None or s["hidden"].shape != hidden_roots.shape or s["hidden"].dtype != hidden_roots.dtype:
+            s["hidden"] = torch.empty(hidden_roots.shape, dtype=hidden_roots.dtype, device=self.device)
+        with torch.cuda.stream(self.copy_in):
+            # the slot's staging buffers were last read by its previous search, which ev_out (waited above) follows
+            if noises is not None:
+                s["noise"].copy_(torch.as_tensor(noises), non_blocking=True)
+            s["reward"].copy_(torch.as_tensor(rewards), non_blocking=True)
+            s["logits"].copy_(torch.as_tensor(logits), non_blocking=True)
+            s["legal"].copy_(torch.as_tensor(legal), non_blocking=True)
+            s["hidden"].copy_(hidden_roots, non_blocking=True)
+            s["ev_in"].record(self.copy_in)
+        self.compute.wait_event(s["ev_in"])
+        with torch.cuda.stream(self.compute):
+            if noises is not None:
+                s["roots"].prepare(fraction, s["noise"], s["reward"], s["logits"], s["legal"])
+            else:
+                s["roots"].prepare_no_noise(s["reward"], s["logits"], s["legal"])
+            self.mcts.run_multi(s["roots"], self.model, s["hidden"])
+            check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, self.compute.cuda_stream, ptr(s["visits"]),
+                                                      ptr(s["values"])))
+            s["ev_done"].record(self.compute)
+        self.copy_out.wait_event(s["ev_done"])
+        with torch.cuda.stream(self.copy_out):
+            out_visits.copy_(s["visits"], non_blocking=True)
+            out_values.copy_(s["values"], non_blocking=True)
+            s["ev_out"].record(self.copy_out)
+        return i
+
+    def wait(self, ticket):
+        self.slots[ticket]["ev_out"].synchronize()
+
+    def drain(self):
+        for s in self.slots:
+            if s["busy"]:
+                s["ev_out"].synchronize()
+                s["busy"] = False
