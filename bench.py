@@ -284,7 +284,7 @@ def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the
     committed `ncu --set full` capture (profiles/); None if the summary is missing."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_ncu_full_k_search_step.csv")
+    path = os.path.join(ROOT, "profiles", "r01b_ncu_full_k_search_step.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
