@@ -116,6 +116,17 @@ def test_full_size_config4_properties_and_oracle():
     assert (gpu.path_lens() >= 2).all()
 
 
+def test_full_size_config5_shard_properties_and_oracle():
+    """BASELINE configs[4] per-GPU shard at 8 GPUs: 2048 Hanabi-Full trees x 200 simulations (4020 node slots per
+    tree, deep paths), lock-step vs the oracle plus the same invariants."""
+    N, A, S = 2048, 20, 200
+    gpu, cpu = _lockstep_vs_oracle(N, A, S, 78, every=40)
+    visits, values, minmax = gpu.stats()
+    assert (visits.sum(1) == S - 1).all()
+    assert (minmax[:, 0] <= minmax[:, 1]).all() and np.isfinite(values).all()
+    assert gpu.path_lens().max() >= 8              # the deep-tree stress really is deep
+
+
 def test_fused_backprop_traverse_equals_separate_calls():
     from hanabizero_b200 import _lib, cytree
     N, A, S = 300, 20, 30
