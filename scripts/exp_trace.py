@@ -43,7 +43,7 @@ for x in range(1, S - 1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); _lib.check(lib.hz_trees_search_step(roots.handle, st, x, 1, ref)); e1.record()
     torch.cuda.synchronize()
-    if x in (25,):
+    if x in (10, 25, 45):
         tr = trace.cpu().numpy().astype(np.float64)
         d = np.diff(tr[:, :7], axis=1)
         depth = tr[:, 7] - 1
@@ -57,3 +57,9 @@ for x in range(1, S - 1):
             print(f"      {nm:24s} mean {dd.mean():8.0f}  p50 {np.median(dd):8.0f}  max {dd.max():8.0f}")
         lv = d[:, 4] / np.maximum(depth, 1)
         print(f"    traverse cycles per level: mean {lv.mean():.0f} p90 {np.percentile(lv, 90):.0f}")
+        start, end = tr[:, 0], tr[:, 6]
+        t0 = start.min()
+        print(f"    warps start within {start.max() - t0:.0f} cycles; end-time percentiles (cycles after first start): "
+              + ", ".join(f"p{q}={np.percentile(end - t0, q):.0f}" for q in (10, 50, 90, 99, 100)))
+        deep = depth >= np.percentile(depth, 99)
+        print(f"    deepest 1% of trees: depth {depth[deep].mean():.1f}, traverse {d[deep, 4].mean():.0f} cycles = {d[deep, 4].mean() / depth[deep].mean():.0f} per level")
