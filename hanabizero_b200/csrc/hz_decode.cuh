@@ -54,45 +54,84 @@ __device__ __forceinline__ Logits8 load_logits8(const T* __restrict__ x, int wid
   return r;
 }
 
-// Whole warp: softmax over the row -> expectation over support -> / delta -> inverse of
-// h(v) = sign(v)(sqrt(|v|+1)-1) + 0.001 v -> * delta, NaN -> 0.  Every lane returns the result.
-// (width <= 256; one fixed summation order shared by every caller, so results are reproducible
-// between the standalone decode kernel and the fused search step.)
+// The decode is not part of the reference's tree engine (its callers do it in PyTorch, core/config.py:210-232), so its
+// bar is float tolerance, not bits: fused multiply-adds and the fast exp2 / reciprocal units are used on purpose —
+// this code runs once per tree per simulation inside an issue-bound kernel.  One arithmetic sequence is shared by the
+// standalone kernel and the fused search step, so the two paths agree bit for bit.
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// this lane's eight support values (zero past the row's width)
+__device__ __forceinline__ void load_support8(const float* __restrict__ support, int width, int c0, float sp[8]) {
+  if (c0 + 8 <= width && ((reinterpret_cast<uintptr_t>(support + c0) & 15) == 0)) {
+    const float4 a = *reinterpret_cast<const float4*>(support + c0), b = *reinterpret_cast<const float4*>(support + c0 + 4);
+    sp[0] = a.x; sp[1] = a.y; sp[2] = a.z; sp[3] = a.w; sp[4] = b.x; sp[5] = b.y; sp[6] = b.z; sp[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sp[k] = (c0 + k < width) ? support[c0 + k] : 0.0f;
+  }
+}
+
+// per-lane partial sums of exp(x - m) and exp(x - m) * support; absent columns hold -inf and contribute exp2(-inf) = 0
+__device__ __forceinline__ void decode_partial(const Logits8& x, const float sp[8], float m, float& se, float& sw) {
+  const float kLog2e = 1.4426950408889634f;
+  const float nm = -m * kLog2e;
+  se = 0.0f;
+  sw = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float e = fast_exp2(__fmaf_rn(x.v[k], kLog2e, nm));
+    se += e;
+    sw = __fmaf_rn(e, sp[k], sw);
+  }
+}
+
+// expectation -> / delta -> inverse of h(v) = sign(v)(sqrt(|v|+1)-1) + 0.001 v -> * delta, NaN -> 0
+__device__ __forceinline__ float decode_finish(float se, float sw, float delta) {
+  const float eps = 0.001f;
+  const float v = __fdividef(__fdividef(sw, se), delta);
+  float r = (fast_sqrt(__fmaf_rn(4.0f * eps, fabsf(v) + 1.0f + eps, 1.0f)) - 1.0f) * (1.0f / (2.0f * eps));
+  r = __fmaf_rn(r, r, -1.0f);
+  r = (v < 0.0f ? -r : r) * delta;
+  return (r != r) ? 0.0f : r;
+}
+
+// Whole warp: softmax over the row -> expectation over support -> inverse transform.  Every lane returns the result.
+// (width <= 256; one fixed summation order shared by every caller.)
 __device__ __forceinline__ float warp_decode8(const Logits8& x, const float* __restrict__ support, int width,
                                               float delta, int lane) {
-  const int c0 = lane * 8;
+  float sp[8];
+  load_support8(support, width, lane * 8, sp);
   float m = x.v[0];
 #pragma unroll
   for (int k = 1; k < 8; ++k) m = fmaxf(m, x.v[k]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(HZ_FULL, m, o));
-  float se = 0.0f, sw = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (c0 + k < width) {
-      const float e = __expf(x.v[k] - m);   // decode tolerance is float-level, not bit-level (network output)
-      se += e;
-      sw += e * support[c0 + k];
-    }
-  }
+  float se, sw;
+  decode_partial(x, sp, m, se, sw);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     se += __shfl_xor_sync(HZ_FULL, se, o);
     sw += __shfl_xor_sync(HZ_FULL, sw, o);
   }
-  const float eps = 0.001f;
-  const float v = (sw / se) / delta;
-  float r = (sqrtf(1.0f + 4.0f * eps * (fabsf(v) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
-  r = r * r - 1.0f;
-  r = (v < 0.0f ? -r : r) * delta;
-  return (r != r) ? 0.0f : r;
+  return decode_finish(se, sw, delta);
 }
 
 // Two rows at once (value and reward of one tree): the same arithmetic per row as warp_decode8, with the
 // two rows' shuffle reductions issued side by side so their latencies overlap.
 __device__ __forceinline__ void warp_decode8_pair(const Logits8& xa, const Logits8& xb, const float* __restrict__ support,
                                                   int width, float delta, int lane, float& out_a, float& out_b) {
-  const int c0 = lane * 8;
+  float sp[8];
+  load_support8(support, width, lane * 8, sp);
   float ma = xa.v[0], mb = xb.v[0];
 #pragma unroll
   for (int k = 1; k < 8; ++k) {
@@ -105,18 +144,9 @@ __device__ __forceinline__ void warp_decode8_pair(const Logits8& xa, const Logit
     ma = fmaxf(ma, ta);
     mb = fmaxf(mb, tb);
   }
-  float sea = 0.0f, swa = 0.0f, seb = 0.0f, swb = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (c0 + k < width) {
-      const float sp = support[c0 + k];
-      const float ea = __expf(xa.v[k] - ma), eb = __expf(xb.v[k] - mb);
-      sea += ea;
-      swa += ea * sp;
-      seb += eb;
-      swb += eb * sp;
-    }
-  }
+  float sea, swa, seb, swb;
+  decode_partial(xa, sp, ma, sea, swa);
+  decode_partial(xb, sp, mb, seb, swb);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float t0 = __shfl_xor_sync(HZ_FULL, sea, o), t1 = __shfl_xor_sync(HZ_FULL, swa, o);
@@ -126,16 +156,8 @@ __device__ __forceinline__ void warp_decode8_pair(const Logits8& xa, const Logit
     seb += t2;
     swb += t3;
   }
-  const float eps = 0.001f;
-  const float va = (swa / sea) / delta, vb = (swb / seb) / delta;
-  float ra = (sqrtf(1.0f + 4.0f * eps * (fabsf(va) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
-  float rb = (sqrtf(1.0f + 4.0f * eps * (fabsf(vb) + 1.0f + eps)) - 1.0f) / (2.0f * eps);
-  ra = ra * ra - 1.0f;
-  rb = rb * rb - 1.0f;
-  ra = (va < 0.0f ? -ra : ra) * delta;
-  rb = (vb < 0.0f ? -rb : rb) * delta;
-  out_a = (ra != ra) ? 0.0f : ra;
-  out_b = (rb != rb) ? 0.0f : rb;
+  out_a = decode_finish(sea, swa, delta);
+  out_b = decode_finish(seb, swb, delta);
 }
 
 template <typename T>
