@@ -19,6 +19,14 @@
 
 namespace hz {
 
+#ifdef HZ_TRACE
+// debug build only: per-game cycle stamps of the env kernel's phases (scripts/exp_env_trace.py)
+__device__ long long* g_env_trace = nullptr;
+#define HZ_ESTAMP(k) do { if (g_env_trace && lane == 0) g_env_trace[(size_t)gi * 16 + (k)] = clock64(); } while (0)
+#else
+#define HZ_ESTAMP(k) do { } while (0)
+#endif
+
 constexpr int kEnvWarps = 4;
 constexpr int kStateBytes = 128;
 constexpr int P = 2;  // both reference presets are 2-player
@@ -117,33 +125,35 @@ __device__ __forceinline__ void advance(uint8_t* st, int H) {  // hanabi_state.c
 // (hanabi_game.cc:106-112, libstdc++ discrete_distribution + generate_canonical<double,53>) ->
 // ApplyMove(kDeal) (221-243).  Warp-cooperative; all lanes must call.  scratch: 64 doubles of shared
 // memory per warp.  The two ordered fp64 sums (std::accumulate, std::partial_sum) are evaluated in
-// libstdc++'s order, but by every lane on its own prefix of the compacted outcome list, so no
-// shuffle sits on the add chain.
+// libstdc++'s order over ALL NT card types instead of the compacted outcome list: a type the deck no
+// longer holds contributes +0.0, and adding +0.0 to a non-negative double is exact, so the bits are
+// the same — but the trip counts are compile-time constants, the loops unroll, the operand loads
+// leave the add chain, and there is no divergence.  (A finished game re-deals ten cards inside the
+// launch: these chains are the tail of the kernel.)
+template <int NT>
 __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_t* mt, int& mti, MtWindow& win,
                                             double* scratch, int lane) {
-  const int n_types = g.C * g.R;
-  const int cnt = lane < n_types ? st[O_DECKCNT + lane] : 0;
+  const int cnt = lane < NT ? st[O_DECKCNT + lane] : 0;
   const bool have = cnt > 0;
   const unsigned mask = __ballot_sync(HZ_FULL, have);
   const int m = __popc(mask);
   int pick = __ffs(mask) - 1;  // single outcome: _M_prob.size() < 2 -> index 0, no draw consumed
   if (m >= 2) {
-    const int pos = __popc(mask & ((1u << lane) - 1u));   // index of this lane's outcome in the list
-    double* w = scratch;        // [m] ChanceOutcomeProb
-    double* qn = scratch + 32;  // [m] normalised
+    double* w = scratch;        // [32] ChanceOutcomeProb per card type (0.0 where the deck holds none)
+    double* qn = scratch + 32;  // [32] normalised
     const double wv = have ? __ddiv_rn((double)cnt, (double)st[O_DECK]) : 0.0;
-    if (have) w[pos] = wv;
+    w[lane] = wv;
     __syncwarp();
     double sum = 0.0;  // std::accumulate ascending
-    for (int i = 0; i < m; ++i) sum = __dadd_rn(sum, w[i]);
-    if (have) qn[pos] = __ddiv_rn(wv, sum);  // __normalize
+#pragma unroll
+    for (int i = 0; i < NT; ++i) sum = __dadd_rn(sum, w[i]);
+    qn[lane] = have ? __ddiv_rn(wv, sum) : 0.0;  // __normalize
     __syncwarp();
-    double cp = 2.0;  // std::partial_sum ascending; lanes without an outcome never match
-    if (have) {
-      double acc = qn[0];
-      for (int i = 1; i <= pos; ++i) acc = __dadd_rn(acc, qn[i]);
-      cp = (pos == m - 1) ? 1.0 : acc;  // _M_cp.back() = 1.0
-    }
+    double acc = 0.0;  // std::partial_sum ascending, this lane's prefix
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc = __dadd_rn(acc, i <= lane ? qn[i] : 0.0);
+    // lanes without an outcome never match; _M_cp.back() = 1.0
+    const double cp = !have ? 2.0 : (lane == 31 - __clz(mask) ? 1.0 : acc);
     const uint32_t u0 = mt_draw(mt, mti, win, lane);
     const uint32_t u1 = mt_draw(mt, mti, win, lane);
     double p = __dadd_rn((double)u0, __dmul_rn((double)u1, 4294967296.0));
@@ -441,7 +451,7 @@ struct EnvArgs {
 };
 
 template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
-__global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs a) {
+__global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvArgs a) {
   using L = ObsLayout<C, R, H, MI, ML>;
   __shared__ uint32_t s_state[kEnvWarps][kStateBytes / 4];
   __shared__ double s_scratch[kEnvWarps][64];
@@ -461,10 +471,11 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
   MtWindow win = mt_prefetch(mt, mti, lane);
   __syncwarp();
   bool dirty = false;
+  HZ_ESTAMP(0);
 
   if (RESET && (a.reset_mask == nullptr || a.reset_mask[gi])) {  // rl_env.py:249-252
     new_state(st, g, lane);
-    while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, win, scratch, lane);
+    while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
     dirty = true;
   }
   if (STEP && (a.active == nullptr || a.active[gi])) {  // rl_env.py:413-438
@@ -475,17 +486,24 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
       done = is_terminal(st, g);
     } else {
       const int last_score = score;
+      HZ_ESTAMP(1);
       if (lane == 0) apply_move(st, g, action);
       __syncwarp();
-      while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, win, scratch, lane);
+      HZ_ESTAMP(2);
+      while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
+      HZ_ESTAMP(3);
       score = score_of(st, C);
       reward = score - last_score;
       done = is_terminal(st, g);
       dirty = true;
       if (done && a.auto_reset) {
         new_state(st, g, lane);
-        while ((int8_t)st[O_CUR] == -1) deal_random(st, g, mt, mti, win, scratch, lane);
+        while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
+#ifdef HZ_TRACE
+        if (g_env_trace && lane == 0) g_env_trace[(size_t)gi * 16 + 9] = 1;
+#endif
       }
+      HZ_ESTAMP(4);
     }
     if (lane == 0) {
       if (a.out_reward) a.out_reward[gi] = reward;
@@ -498,6 +516,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
     gstate[lane] = s_state[warp][lane];
     if (lane == 0 && mti != mti0) ev.mti[gi] = mti;
   }
+  HZ_ESTAMP(5);
   if (OBSERVE) {
     constexpr int BPC = C * R;
     const int cur = (int8_t)st[O_CUR];
@@ -506,6 +525,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
     __syncwarp();
     for (int seg = lane; seg < L::SEGS; seg += HZ_WARP) obs_segment<C, R, H, MI, ML>(st, cur, words, seg);
     __syncwarp();
+    HZ_ESTAMP(6);
     float* og = a.out_global ? a.out_global + (size_t)gi * a.ld_global : nullptr;
     float* ol = a.out_local ? a.out_local + (size_t)gi * a.ld_local : nullptr;
     if (og || ol) {
@@ -523,6 +543,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
     uint8_t* ol8 = a.out_local8 ? a.out_local8 + (size_t)gi * a.ld_local : nullptr;
     if (og8) store_bits_u8(og8, words, 0, L::GLOBAL, lane);
     if (ol8) store_bits_u8(ol8, words, L::OWN, L::GLOBAL - L::OWN, lane);
+    HZ_ESTAMP(7);
     if (a.out_legal || a.out_legal8) {
       // LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all uids at once: lanes first agree on
       // which colours / ranks the partner's hand holds, then each lane tests its own move id
@@ -540,6 +561,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP) k_env(EnvView ev, EnvArgs 
         if (a.out_legal8) a.out_legal8[(size_t)gi * g.A + lane] = ok ? 1 : 0;
       }
     }
+    HZ_ESTAMP(8);
     if (a.out_dump && lane == 0) {  // layout of oracle/hanabi_oracle.c:ohanabi_dump
       int32_t* o = a.out_dump + (size_t)gi * (5 + C + 2 * BPC + P * (1 + 5 * H));
       int n = 0;
@@ -757,6 +779,12 @@ int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, co
   a.out_local8 = out_local; a.ld_local = ld_local; a.out_legal8 = out_legal;
   return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
 }
+
+#ifdef HZ_TRACE
+int hz_debug_set_env_trace(long long* dev_buf) {   // debug build only (not in include/hzb200.h)
+  return cudaMemcpyToSymbol(g_env_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? HZ_OK : HZ_ERR_CUDA;
+}
+#endif
 
 int hz_envs_check(hz_envs* e, void* stream, int32_t* out_game) {
   if (!e) { set_error("hz_envs_check: NULL handle"); return HZ_ERR_ARG; }
