@@ -149,3 +149,55 @@ class SelfPlayEngine:
         self._push(out["done"])
         self.recorder.begin(self._obs, self.legal, mask=out["done"])
         return out
+
+
+@torch.no_grad()
+def evaluate(model, config, num_episodes, hanabi_name="Hanabi-Full", seeds=None, mdp="global", stack=4, max_moves=1000,
+             device=None):
+    """The evaluation caller of the search (/root/reference/core/test.py:44-126, `test`): `num_episodes` games played to
+    the end on the device — noise-free roots (prepare_no_noise), arg-max of the visit counts, finished games stop
+    (no re-deal) — one batched search per move.  Returns (final_scores, moves): two int lists, final_scores[i] being
+    info['score'] of game i's last step as the reference records it (ep_final_rewards)."""
+    env = HanabiVecEnv(num_episodes, hanabi_name, seeds, device=device)
+    dev, n, a = env.device, num_episodes, env.num_actions
+    lib = _lib.load()
+    obs_dim = env.global_dim if mdp == "global" else env.local_dim
+    frames = torch.zeros(n, stack, obs_dim, device=dev)
+    obs = torch.zeros(n, obs_dim, device=dev)
+    legal = torch.zeros(n, a, device=dev)
+    g, l = (obs, None) if mdp == "global" else (None, obs)
+    st = lambda: torch.cuda.current_stream(dev).cuda_stream
+    env.reset_all(observe=False)
+    check(lib.hz_envs_observe(env._h, st(), ptr(g), 0 if g is None else g.stride(0), ptr(l),
+                              0 if l is None else l.stride(0), ptr(legal)))
+    all_games = torch.ones(n, dtype=torch.uint8, device=dev)
+    check(lib.hz_stack_push(st(), ptr(frames), ptr(obs), obs.stride(0), ptr(all_games), n, stack, obs_dim))
+    alive = torch.ones(n, dtype=torch.uint8, device=dev)
+    final = torch.zeros(n, dtype=torch.int32, device=dev)
+    moves = torch.zeros(n, dtype=torch.int32, device=dev)
+    mcts = MCTS(config)
+    model.eval()
+    amp = getattr(config, "amp_type", "none") == "torch_amp"
+    zeros = torch.zeros(n, device=dev)
+    never = torch.zeros(n, dtype=torch.uint8, device=dev)
+    for _ in range(max_moves):
+        if not bool(alive.any()):
+            break
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            _, logits, hidden = model.initial_inference_device(frames.view(n, -1))
+        roots = cytree.Roots(n, a, config.num_simulations, device=dev)
+        roots.prepare_no_noise(zeros, logits.float(), legal.int())
+        mcts.run_multi(roots, model, hidden)
+        visits, _ = roots.get_stats_tensors()
+        actions, _ = select_action_batch(visits, legal, 1.0, deterministic=True)
+        # finished games are not stepped (test.py:99-100) and keep their last observation
+        _, _, _, reward, done, score = env.step_all(actions, active=alive, out_global=g, out_local=l, out_legal=legal,
+                                                    want_global=g is not None, want_local=l is not None)
+        stepped = alive.bool()
+        finished = stepped & done.bool()
+        final = torch.where(finished, score, final)
+        moves += stepped.int()
+        check(lib.hz_stack_push(st(), ptr(frames), ptr(obs), obs.stride(0), ptr(never), n, stack, obs_dim))
+        alive = (stepped & ~done.bool()).to(torch.uint8)
+    env.check()
+    return final.cpu().tolist(), moves.cpu().tolist()

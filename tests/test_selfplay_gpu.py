@@ -101,3 +101,49 @@ def test_selfplay_engine_steps_on_device(mdp):
         ref_obs = eng.env.observe()[0 if mdp == "global" else 1]
         assert torch.equal(eng.frames[:, -1], ref_obs)
     eng.env.check()
+
+
+def test_evaluate_equals_a_reference_style_host_loop():
+    """evaluate() (core/test.py:44-126 on the device) against the same loop written the reference's way: scalar
+    HanabiEnv objects behind HanabiControlWrapper, list-based cytree calls, the scalar select_action."""
+    from hanabizero_b200 import cytree
+    from hanabizero_b200.env_wrapper import HanabiControlWrapper
+    from hanabizero_b200.hanabi_env import HanabiEnv
+    from hanabizero_b200.mcts import MCTS, SearchConfig
+    from hanabizero_b200.model import MuZeroNet
+    from hanabizero_b200.selfplay import evaluate, select_action
+    N, S, stack, A = 6, 8, 4, 11
+    torch.manual_seed(0)
+    model = MuZeroNet(193 * stack, A).randomize_heads().cuda().eval()
+    cfg = SearchConfig(num_simulations=S)
+    seeds = [3, 4, 5, 6, 7, 8]
+    scores, moves = evaluate(model, cfg, N, "Hanabi-Small", seeds=seeds, mdp="global", stack=stack)
+
+    envs = [HanabiControlWrapper(HanabiEnv({"hanabi_name": "Hanabi-Small", "seed": s}), 0.999, mdp="global") for s in seeds]
+    windows, legals = [], []
+    for env in envs:
+        o, la = env.reset()
+        windows.append([o] * stack)
+        legals.append(la)
+    dones = np.zeros(N, bool)
+    ref_scores, ref_moves = [0] * N, [0] * N
+    while not dones.all():
+        stack_obs = torch.from_numpy(np.array(windows)).cuda().reshape(N, -1)
+        out = model.initial_inference(stack_obs.float())
+        roots = cytree.Roots(N, A, S)
+        roots.prepare_no_noise(out.reward, out.policy_logits.tolist(), legals)
+        MCTS(cfg).run_multi(roots, model, out.hidden_state)
+        dist = roots.get_distributions()
+        for i in range(N):
+            if dones[i]:
+                continue
+            action, _ = select_action(dist[i], temperature=1, deterministic=True, legal_actions=legals[i])
+            o, r, d, info, la = envs[i].step(int(action))
+            windows[i] = windows[i][1:] + [o]
+            legals[i] = la
+            dones[i] = bool(d)
+            ref_moves[i] += 1
+            if dones[i]:
+                ref_scores[i] = info.item()["score"]
+    assert scores == ref_scores and moves == ref_moves
+    assert all(m >= 1 for m in moves)
