@@ -9,6 +9,11 @@ container only (needs /root/reference and `make -C oracle ref`):
   numpy >= 1.24, used at rl_env.py:256,429) and a stub gym.spaces.Discrete (rl_env.py:21).
 * tree_*.npz  — lock-step MCTS traces from the reference tree engine compiled with the rand()==0
   shim (oracle/_ref/libref_ctree_det.so), inputs included.
+* traj_*.npz  — self-play bookkeeping by the reference's own Python: core/game.py GameHistory
+  (init / store_search_stats / append / game_over), core/utils.py select_action and the turn-reward
+  loop of core/selfplay_worker.py DataWorker.put, driven over episodes of the reference env with
+  synthetic search results.  Import stubs only for modules that are not on this path (ray.put/get
+  as identity, cv2, gym base classes, the compiled cytree).
 
 Nothing here runs on the GPU box; the fixtures are what travels.
 """
@@ -143,6 +148,111 @@ def make_tree(N, A, S, seed, tag, noise=True, mask_mode="random", store_inputs=T
     print(path, "root0", visits[0].tolist(), repr(float(values[0])))
 
 
+def import_reference_selfplay():
+    """core.game.GameHistory, core.utils.select_action and DataWorker.put from /root/reference, unmodified."""
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Any:
+        def __init__(self, *a, **k):
+            pass
+
+        def __getattr__(self, n):
+            return _Any()
+
+        def __call__(self, *a, **k):
+            return _Any()
+
+    stub("ray", put=lambda x: x, get=lambda x: x,
+         remote=lambda *a, **k: (a[0] if a and callable(a[0]) and not k else (lambda c: c)))
+    stub("cv2", ocl=_Any(), setNumThreads=lambda n: None)
+    gym = sys.modules["gym"]
+    for base in ("Wrapper", "ObservationWrapper", "RewardWrapper", "Env"):
+        setattr(gym, base, object)
+    gym.spaces.Box = _Any
+    stub("core.mcts", MCTS=None)
+    stub("core.model", concat_output=None, concat_output_value=None)
+    import core
+    ctree = stub("core.ctree")
+    ctree.__path__ = []
+    ctree.cytree = stub("core.ctree.cytree", Node=None, Roots=None)
+    core.ctree = ctree
+    from core.game import GameHistory
+    from core.utils import select_action
+    try:
+        from core.selfplay_worker import DataWorker
+        put = DataWorker.put
+    except Exception as e:  # the module pulls in the whole training stack; the loop is restated if it cannot load
+        print("core.selfplay_worker not importable here (%s: %s); using the restated turn-reward loop" % (type(e).__name__, e))
+
+        def put(self, data):  # core/selfplay_worker.py:29-39
+            game_histories, _ = data
+            prev_r = game_histories.rewards[0]
+            for step_id in range(1, len(game_histories.rewards)):
+                cur_r = game_histories.rewards[step_id] + prev_r
+                prev_r = game_histories.rewards[step_id]
+                game_histories.rewards[step_id] = cur_r
+            self.trajectory_pool.append(data)
+    return GameHistory, select_action, put
+
+
+def make_traj(HanabiEnv, ref, name, seed, episodes, mode, tag, stack=4):
+    GameHistory, select_action, put = ref
+    env = HanabiEnv({"hanabi_name": name, "seed": seed})
+    A, h = env.num_moves(), env.game.hand_size()
+    rng = np.random.default_rng(77 * seed + episodes)
+    cfg = types.SimpleNamespace(stacked_observations=stack, discount=0.999, action_space_size=A)
+    worker = types.SimpleNamespace(trajectory_pool=[])
+    rec = dict(obs=[], legal=[], visits=[], value=[], action=[], reward=[], done=[])
+    eps = []
+    for ep in range(episodes):
+        share_obs, _, legal = env.reset()
+        obs, legal = np.array(share_obs), np.array(legal)
+        rec["obs"].append(obs); rec["legal"].append(legal)          # the observation / mask an episode starts from
+        rec["visits"].append(np.zeros(A, np.int32)); rec["value"].append(0.0); rec["action"].append(-1)
+        rec["reward"].append(0); rec["done"].append(0)
+        gh = GameHistory(types.SimpleNamespace(n=A), max_length=1000, config=cfg)
+        gh.init([obs for _ in range(stack)], legal)
+        done = False
+        while not done:
+            # synthetic search result: visit counts favour the scripted policy's move, some land on illegal moves
+            want = policy(mode, rng, h, legal, playable_from_env(env))
+            visits = rng.integers(0, 12, A).astype(np.int32)
+            visits[want] = 40
+            value = float(np.float32(rng.standard_normal()))
+            dist = visits.tolist()
+            action, _ = select_action(dist, temperature=1, deterministic=True, legal_actions=legal)
+            share_obs, _, reward, done, info, legal_next = env.step(int(action))
+            obs, legal_next = np.array(share_obs), np.array(legal_next)
+            gh.store_search_stats(dist, value)                      # dist was mutated by select_action, as in the worker
+            gh.append(action, obs, reward, legal_next)
+            rec["obs"].append(obs); rec["legal"].append(legal_next); rec["visits"].append(visits)
+            rec["value"].append(value); rec["action"].append(int(action)); rec["reward"].append(int(reward))
+            rec["done"].append(int(done))
+            legal = legal_next
+        gh.game_over()
+        put(worker, (gh, None))
+        eps.append(gh)
+    o = np.asarray(rec["obs"], np.uint8)
+    out = dict(preset=0 if name == "Hanabi-Full" else 1, seed=seed, mode=mode, stack=stack, actions=A,
+               obs_bits=np.packbits(o, axis=1), obs_dim=o.shape[1], legal=np.asarray(rec["legal"], np.uint8),
+               visits=np.asarray(rec["visits"], np.int32), value=np.asarray(rec["value"], np.float32),
+               action=np.asarray(rec["action"], np.int32), reward=np.asarray(rec["reward"], np.int32),
+               done=np.asarray(rec["done"], np.uint8), ep_len=np.asarray([len(g.actions) for g in eps], np.int32),
+               out_vis=np.concatenate([np.asarray(g.child_visits, np.float64) for g in eps]),
+               out_root=np.concatenate([np.asarray(g.root_values, np.float64) for g in eps]),
+               out_a=np.concatenate([np.asarray(g.actions, np.int64) for g in eps]),
+               out_r=np.concatenate([np.asarray(g.rewards, np.int64) for g in eps]),
+               out_o_bits=np.packbits(np.concatenate([np.asarray(g.obs_history, np.uint8) for g in eps]), axis=1),
+               out_la=np.concatenate([np.asarray(g.legal_actions, np.float64) for g in eps]))
+    path = os.path.join(OUT, f"traj_{tag}.npz")
+    np.savez_compressed(path, **out)
+    print(path, "episodes", episodes, "moves", out["ep_len"].tolist())
+
+
 if __name__ == "__main__":
     make_tree(8, 20, 50, 1234, "full_n8_s50")
     make_tree(16, 11, 50, 7, "small_n16_s50")
@@ -157,3 +267,6 @@ if __name__ == "__main__":
     make_env(HanabiEnv, "Hanabi-Full", 3, 4, "random", "full_seed3_random")
     make_env(HanabiEnv, "Hanabi-Small", 2, 4, "smart", "small_seed2_smart")
     make_env(HanabiEnv, "Hanabi-Small", 3, 6, "random", "small_seed3_random")
+    ref = import_reference_selfplay()
+    make_traj(HanabiEnv, ref, "Hanabi-Small", 4, 5, "random", "small_seed4")
+    make_traj(HanabiEnv, ref, "Hanabi-Full", 5, 2, "smart", "full_seed5")

@@ -103,3 +103,78 @@ def unpack_env_golden(g):
     glob_ = np.unpackbits(g["glob_bits"], axis=1)[:, :int(g["glob_dim"])]
     loc = np.unpackbits(g["loc_bits"], axis=1)[:, :int(g["loc_dim"])]
     return glob_, loc
+
+
+class RefGameHistory:
+    """The fields of core/game.py:49-215 that self-play writes, as the reference writes them (test-side port)."""
+
+    def __init__(self, stack):
+        self.stack = stack
+
+    def init(self, init_observations, init_legal_action):            # game.py:73-93
+        assert len(init_observations) == self.stack
+        self.child_visits, self.root_values, self.actions, self.rewards = [], [], [], []
+        self.obs_history = [np.array(o, copy=True) for o in init_observations]
+        self.legal_actions = [init_legal_action]
+
+    def store_search_stats(self, visit_counts, root_value):          # game.py:189-204 (idx is None)
+        sum_visits = sum(visit_counts)
+        self.child_visits.append([visit_count / sum_visits for visit_count in visit_counts])
+        self.root_values.append(root_value)
+
+    def append(self, action, obs, reward, legal_action):             # game.py:143-148
+        self.actions.append(action)
+        self.obs_history.append(obs)
+        self.rewards.append(reward)
+        self.legal_actions.append(legal_action)
+
+    def game_over(self):                                             # game.py:176-187
+        self.rewards = np.array(self.rewards)
+        self.obs_history = np.array(self.obs_history)
+        self.actions = np.array(self.actions)
+        self.child_visits = np.array(self.child_visits)
+        self.root_values = np.array(self.root_values)
+        self.legal_actions = np.array(self.legal_actions)
+
+    def put(self):                                                   # selfplay_worker.py:29-39
+        prev_r = self.rewards[0]
+        for step_id in range(1, len(self.rewards)):
+            cur_r = self.rewards[step_id] + prev_r
+            prev_r = self.rewards[step_id]
+            self.rewards[step_id] = cur_r
+
+
+
+def ref_select_action(visit_counts, temperature, deterministic, legal_actions, u):
+    """core/utils.py:280-295 with np.random.choice replaced by its own algorithm for a given uniform u."""
+    visit_counts = list(visit_counts)
+    for i in range(len(legal_actions)):
+        if legal_actions[i] == 0 and visit_counts[i] >= 1:
+            visit_counts[i] = 0
+    probs = [float(v) ** (1 / temperature) for v in visit_counts]
+    total = sum(probs)
+    probs = [x / total for x in probs]
+    if deterministic:
+        action = int(np.argmax(visit_counts))
+    else:
+        cdf = np.cumsum(np.asarray(probs, np.float64))
+        cdf /= cdf[-1]
+        action = int(np.searchsorted(cdf, u, side="right"))
+    pk = np.asarray(probs, np.float64)
+    pk = pk / pk.sum()
+    ent = float(-(pk[pk > 0] * np.log(pk[pk > 0])).sum() / np.log(2))
+    return action, ent, visit_counts
+
+
+def unpack_traj_golden(g):
+    """-> (per-step observations [T, D] uint8, list of per-episode dicts in GameHistory.save_file's layout)."""
+    D, stack = int(g["obs_dim"]), int(g["stack"])
+    obs = np.unpackbits(g["obs_bits"], axis=1)[:, :D]
+    out_o = np.unpackbits(g["out_o_bits"], axis=1)[:, :D]
+    eps, s, so, sl = [], 0, 0, 0
+    for n in g["ep_len"]:
+        n = int(n)
+        eps.append(dict(vis=g["out_vis"][s:s + n], root=g["out_root"][s:s + n], a=g["out_a"][s:s + n],
+                        r=g["out_r"][s:s + n], o=out_o[so:so + stack + n], la=g["out_la"][sl:sl + n + 1]))
+        s, so, sl = s + n, so + stack + n, sl + n + 1
+    return obs, eps

@@ -4,28 +4,9 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import ref_select_action
+
 pytestmark = pytest.mark.gpu
-
-
-def ref_select_action(visit_counts, temperature, deterministic, legal_actions, u):
-    """core/utils.py:280-295 with np.random.choice replaced by its own algorithm for a given uniform u."""
-    visit_counts = list(visit_counts)
-    for i in range(len(legal_actions)):
-        if legal_actions[i] == 0 and visit_counts[i] >= 1:
-            visit_counts[i] = 0
-    probs = [float(v) ** (1 / temperature) for v in visit_counts]
-    total = sum(probs)
-    probs = [x / total for x in probs]
-    if deterministic:
-        action = int(np.argmax(visit_counts))
-    else:
-        cdf = np.cumsum(np.asarray(probs, np.float64))
-        cdf /= cdf[-1]
-        action = int(np.searchsorted(cdf, u, side="right"))
-    pk = np.asarray(probs, np.float64)
-    pk = pk / pk.sum()
-    ent = float(-(pk[pk > 0] * np.log(pk[pk > 0])).sum() / np.log(2))
-    return action, ent, visit_counts
 
 
 @pytest.mark.parametrize("temperature", [1.0, 0.5, 0.25])

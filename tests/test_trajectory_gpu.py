@@ -4,46 +4,9 @@ import numpy as np
 import pytest
 import torch
 
+from helpers import RefGameHistory, golden_files, load_golden, ref_select_action, unpack_traj_golden
+
 pytestmark = pytest.mark.gpu
-
-
-class RefGameHistory:
-    """The fields of core/game.py:49-215 that self-play writes, as the reference writes them (test-side port)."""
-
-    def __init__(self, stack):
-        self.stack = stack
-
-    def init(self, init_observations, init_legal_action):            # game.py:73-93
-        assert len(init_observations) == self.stack
-        self.child_visits, self.root_values, self.actions, self.rewards = [], [], [], []
-        self.obs_history = [np.array(o, copy=True) for o in init_observations]
-        self.legal_actions = [init_legal_action]
-
-    def store_search_stats(self, visit_counts, root_value):          # game.py:189-204 (idx is None)
-        sum_visits = sum(visit_counts)
-        self.child_visits.append([visit_count / sum_visits for visit_count in visit_counts])
-        self.root_values.append(root_value)
-
-    def append(self, action, obs, reward, legal_action):             # game.py:143-148
-        self.actions.append(action)
-        self.obs_history.append(obs)
-        self.rewards.append(reward)
-        self.legal_actions.append(legal_action)
-
-    def game_over(self):                                             # game.py:176-187
-        self.rewards = np.array(self.rewards)
-        self.obs_history = np.array(self.obs_history)
-        self.actions = np.array(self.actions)
-        self.child_visits = np.array(self.child_visits)
-        self.root_values = np.array(self.root_values)
-        self.legal_actions = np.array(self.legal_actions)
-
-    def put(self):                                                   # selfplay_worker.py:29-39
-        prev_r = self.rewards[0]
-        for step_id in range(1, len(self.rewards)):
-            cur_r = self.rewards[step_id] + prev_r
-            prev_r = self.rewards[step_id]
-            self.rewards[step_id] = cur_r
 
 
 def _same(ep, ref):
@@ -230,3 +193,37 @@ def test_reanalyze_policies_equal_a_direct_search():
     assert all(sum(d) == S - 1 for d in dist)
     draws = reanalyze_policies(cfg, model, obs, legal, mask, unroll, as_tensor=True)      # device noise draw
     assert draws.is_cuda and torch.allclose(draws.sum(-1).view(-1), torch.from_numpy(mask.astype(np.float64)).cuda())
+
+
+@pytest.mark.parametrize("name", golden_files("traj_"))
+def test_recorder_and_select_action_replay_reference_trajectories(name):
+    """Fixtures written by the reference's own GameHistory / select_action / DataWorker.put (tests/golden/make_golden.py):
+    the same per-move search results go through hz_select_action and the recorder kernels; actions, mutated visit
+    distributions, observations, turn rewards, root values and legal masks must come out as the reference stored them."""
+    from hanabizero_b200.selfplay import select_action_batch
+    from hanabizero_b200.trajectory import TrajectoryRecorder
+    g = load_golden(name)
+    obs, eps = unpack_traj_golden(g)
+    A, stack, D = int(g["actions"]), int(g["stack"]), int(g["obs_dim"])
+    rec = TrajectoryRecorder(1, D, A, stack, max_len=int(g["ep_len"].max()) + 1)
+    cuda = lambda x, dt: torch.as_tensor(np.ascontiguousarray(x), dtype=dt).cuda().view(1, -1)
+    got = []
+    for t in range(len(g["action"])):
+        o_t, la_t = cuda(obs[t], torch.float32), cuda(g["legal"][t], torch.float32)
+        if g["action"][t] < 0:                      # an episode starts here
+            rec.begin(o_t, la_t)
+            prev_legal = la_t
+            continue
+        visits = cuda(g["visits"][t], torch.int32)
+        action, _ = select_action_batch(visits, prev_legal, 1.0, deterministic=True)
+        assert int(action.item()) == int(g["action"][t]), t
+        rec.append(action, o_t, la_t, cuda([g["reward"][t]], torch.int32).view(-1), visits,
+                   cuda([g["value"][t]], torch.float32).view(-1), cuda([g["done"][t]], torch.uint8).view(-1))
+        prev_legal = la_t
+        if g["done"][t]:
+            got += rec.flush()
+    assert len(got) == len(eps)
+    for ep, want in zip(got, eps):
+        for k in ("vis", "root", "a", "r", "o", "la"):
+            assert ep[k].shape == want[k].shape and (ep[k] == want[k]).all(), k
+        assert ep["vis"].dtype == np.float64
