@@ -93,14 +93,12 @@ if os.environ.get("HZ_CHAIN_TRACE") == "1":
     raw.hz_debug_chain_trace(ch._h, buf.ctypes.data, buf.size)
     t = buf.reshape(grid, 8, 16).astype(np.int64)
     t0 = t[t > 0].min()
-    names = ["pre-wait", "barrier passed", "mma issued", "acc ready", "stores done", "arrived", "tmem drained", "A issued", "A0 in", "Alast in", "W0 in", "Wlast in", "start"]
+    names = ["pre-wait", "barrier passed", "mma issued", "acc ready", "stores done", "arrived", "tmem drained", "A issued", "-", "-", "-", "-", "start"]
     for cta in (0, grid // 2, grid - 1):
         print(f"CTA {cta}: ns since kernel's first stamp")
         for s_ in range(ch.n_steps):
-            print("  step", s_, " ".join(f"{names[j]}={t[cta, s_, j] - t0 if t[cta, s_, j] else -1}" for j in (12, 0, 1, 7, 8, 10, 9, 11, 2, 3, 6, 4, 5)))
+            print("  step", s_, " ".join(f"{names[j]}={t[cta, s_, j] - t0 if t[cta, s_, j] else -1}" for j in (12, 0, 1, 7, 2, 3, 6, 4, 5)))
     arr = t[:, :ch.n_steps, 5]
     print("per-step last arrival - first arrival (ns):", (arr.max(0) - arr.min(0)).tolist())
     print("per-step: last 'arrived' -> median 'barrier passed' of next step (ns):",
           [int(np.median(t[:, s_ + 1, 1]) - arr[:, s_].max()) for s_ in range(ch.n_steps - 1)])
-    print("step 1, CTA 0: after a_full(kb) wait:", (t[0, 7, :8] - t0).tolist())
-    print("step 1, CTA 0: after commit(kb):     ", (t[0, 7, 8:16] - t0).tolist())
