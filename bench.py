@@ -4,14 +4,18 @@ Hanabi env steps/s on 1/2/4/8 B200 next to the reference's host-CPU implementati
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+    python bench.py --config {1..5}                          # BASELINE.json configs[0..4]; default 4
+    python bench.py --scaling weak                           # `trees_total` of the config PER GPU instead of in total
 
 A "step" is one batched search: Roots.prepare + MCTS.run_multi (num_simulations-1 simulations, the
-PyTorch network included, random-init weights with re-drawn heads) + root statistics, over
-`--trees` Hanabi-Full trees per GPU (weak scaling: the root batch is sharded, one model replica per
-GPU, one NCCL all_gather of the final statistics per search).  `value` = simulations/s of the whole
-job with inputs resident in HBM; `e2e` = the same through the list/numpy drop-in API with pinned host
-inputs copied in and statistics copied out inside the timed region.  The Hanabi env is timed the
-same way and reported in the `env` object.  One JSON line is printed by rank 0.
+PyTorch network included, random-init weights with re-drawn heads) + root statistics.  The default is
+BASELINE.json configs[3] AS WRITTEN: 4096 Hanabi-Full trees x 50 simulations IN TOTAL, the root batch sharded
+over the N GPUs (strong scaling: 4096 / N trees per GPU, one model replica per GPU, one NCCL all_gather of the
+final statistics per search, issued off the compute stream).  With N > 1 the line also carries a `weak` object
+(the same search with 4096 trees PER GPU).  `value` = simulations/s of the whole job with inputs resident in
+HBM; `e2e` = the same through the public host-facing API with pinned host inputs copied in and statistics copied
+out inside the timed region.  The Hanabi env is timed the same way and reported in the `env` object.  One JSON
+line is printed by rank 0.
 """
 import argparse
 import json
@@ -32,6 +36,21 @@ import numpy as np  # noqa: E402
 CONST = dict(pb_c_base=19652, pb_c_init=1.25, discount=0.999, delta=0.006, frac=0.25)
 F_HIDDEN = 512
 
+# BASELINE.json configs[0..4]
+CONFIGS = {
+    1: dict(game="Hanabi-Small", mdp="global", trees_total=16, sims=50,
+            name="config 1: Hanabi-Small 2p global MDP, p_mcts_num=16 trees x 50 simulations"),
+    2: dict(game="Hanabi-Full", mdp="global", trees_total=256, sims=50,
+            name="config 2: Hanabi-Full 2p global MDP, 256 trees x 50 simulations"),
+    3: dict(game="Hanabi-Full", mdp="local", trees_total=1024, sims=50,
+            name="config 3: Hanabi-Full 2p local POMDP, stack=4, 1024 trees x 50 simulations"),
+    4: dict(game="Hanabi-Full", mdp="global", trees_total=4096, sims=50,
+            name="config 4: Hanabi-Full 2p global MDP, 4096 trees x 50 simulations"),
+    5: dict(game="Hanabi-Full", mdp="global", trees_total=16384, sims=200,
+            name="config 5: Hanabi-Full 2p global MDP, 16384 trees x 200 simulations (deep-tree stress)"),
+}
+GAMES = {"Hanabi-Full": dict(actions=20, glob=785, loc=660), "Hanabi-Small": dict(actions=11, glob=193, loc=173)}
+
 
 def parse_args():
     p = argparse.ArgumentParser()
@@ -39,43 +58,77 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--trees", type=int, default=4096, help="trees (and games) per GPU")
-    p.add_argument("--sims", type=int, default=50)
+    p.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE.json configs[n-1]")
+    p.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                   help="strong: the config's trees in TOTAL, sharded over the GPUs; weak: that many PER GPU")
+    p.add_argument("--trees-total", type=int, default=None, help="override the config's total tree count")
+    p.add_argument("--trees", type=int, default=None, help="trees (and games) PER GPU (implies --scaling weak)")
+    p.add_argument("--sims", type=int, default=None)
     p.add_argument("--stack", type=int, default=4)
     p.add_argument("--amp", default="torch_amp", choices=["torch_amp", "none"])
-    p.add_argument("--mdp", default="global", choices=["global", "local"], help="observation fed to the network")
+    p.add_argument("--mdp", default=None, choices=["global", "local"], help="observation fed to the network")
     p.add_argument("--env-steps", type=int, default=200, help="env steps per timed env pass")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--quick", action="store_true", help="search + roofline only (skip env / self-play / extras)")
     return p.parse_args()
 
 
+def resolve_workload(args, world):
+    """-> dict(game, A, mdp, sims, scaling, per_gpu, total, name): what one step of this run searches."""
+    c = dict(CONFIGS[args.config])
+    if args.sims is not None:
+        c["sims"] = args.sims
+    if args.mdp is not None:
+        c["mdp"] = args.mdp
+    scaling = args.scaling
+    if args.trees is not None:
+        scaling, per = "weak", args.trees
+    elif scaling == "weak":
+        per = args.trees_total or c["trees_total"]
+    else:
+        total = args.trees_total or c["trees_total"]
+        if total % world:
+            raise SystemExit(f"{total} trees do not shard evenly over {world} GPUs")
+        per = total // world
+    g = GAMES[c["game"]]
+    return dict(game=c["game"], A=g["actions"], mdp=c["mdp"], obs_dim=g["glob"] if c["mdp"] == "global" else g["loc"],
+                sims=c["sims"], scaling=scaling, per_gpu=per, total=per * world, name=c["name"], config=args.config)
+
+
 def b_sim(A, D, s, F):
-    """Algorithmic bytes of one simulation of one tree."""
+    """Algorithmic bytes of one simulation of one tree; F = hidden row in 4-byte units."""
     return D * (16 * A + 32) + 22 * A + 20 * (D + 1) + 12 * s + 32 + 8 * F
 
 
-B_ENV_STEP = 2 * 192 + 4 * 785 + 4 * 20 + 12  # SURVEY.md §8d: state r/w + fp32 global obs + legal + r/d/s
+def b_env_step(obs_dim, A, obs_bytes):
+    """Algorithmic bytes of one env step of one game: state r/w + the observation in the dtype
+    that is actually written + legal mask + reward/done/score."""
+    return 2 * 192 + obs_bytes * obs_dim + obs_bytes * A + 12
 
 
 # ======================================================================================================
 # CPU reference arm (test infrastructure: the ONLY place besides tests/smoke that executes oracle/)
 # ======================================================================================================
+def _load_ref_cytree():
+    import importlib.util
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    so = [f for f in os.listdir(ref_dir) if f.startswith("cytree.") and f.endswith(".so")] if os.path.isdir(ref_dir) else []
+    if not so:
+        return None
+    spec = importlib.util.spec_from_file_location("cytree", os.path.join(ref_dir, so[0]))
+    tree = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tree)
+    return tree
+
+
 def _ref_tree_worker(args):
     """One reference actor: the loop of core/mcts.py:24-55 around the reference's own cytree module
     (oracle/_ref, stock build) with pre-generated network outputs instead of the GPU model —
     Python-list marshalling, host hidden-state gather and .tolist() included, as the reference pays."""
     n, A, S, seed, reps = args
-    import importlib.util
-    ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    so = [f for f in os.listdir(ref_dir) if f.startswith("cytree.") and f.endswith(".so")] if os.path.isdir(ref_dir) else []
-    kind = "reference"
-    if so:
-        spec = importlib.util.spec_from_file_location("cytree", os.path.join(ROOT, "oracle", "_ref", so[0]))
-        tree = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(tree)
-    else:
-        tree, kind = None, "port"
+    tree = _load_ref_cytree()
+    kind = "reference" if tree is not None else "port"
     rng = np.random.default_rng(seed)
     logits0 = rng.standard_normal((n, A)).astype(np.float32)
     noise = rng.dirichlet([0.3] * A, n).astype(np.float32)
@@ -118,53 +171,74 @@ def _ref_tree_worker(args):
 
 
 def _ref_env_worker(args):
-    n_steps, seed = args
+    """The reference's libhanabi in a C++ loop (apply + deal + 2x observe/encode per step, random legal play)."""
+    n_steps, seed, preset = args
     from oracle import loader as L
     kind = "reference" if L.have_ref() else "port"
-    g = L.ref_hanabi(0, seed) if kind == "reference" else L.oracle_hanabi(0, seed)
+    g = L.ref_hanabi(preset, seed) if kind == "reference" else L.oracle_hanabi(preset, seed)
     t0 = time.perf_counter()
     g.play(n_steps, seed + 1)
     return time.perf_counter() - t0, kind
 
 
-def cpu_reference(trees, A, S, cores, reps=1, env_steps_per_core=20000):
+def _ref_pyenv_worker(args):
+    """The reference's Python API (envs/hanabi/rl_env.py:148-442 HanabiEnv.reset/step over pyhanabi.py + cffi +
+    libpyhanabi.so, byte-compiled unmodified into oracle/_ref/refpy): what the reference's callers actually pay
+    per env step.  Random legal play, episodes reset as they end."""
+    n_steps, seed, game = args
+    from oracle import refpy
+    if not refpy.available():
+        return None
+    env = refpy.load_env_class()({"hanabi_name": game, "seed": seed})
+    rng = np.random.default_rng(seed)
+    legal = np.asarray(env.reset()[2])
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        out = env.step(int(rng.choice(np.flatnonzero(legal))))
+        legal = np.asarray(out[5])
+        if out[3]:
+            legal = np.asarray(env.reset()[2])
+    return time.perf_counter() - t0
+
+
+def cpu_reference(trees, A, S, cores, reps=1, env_steps_per_core=20000, game="Hanabi-Full", pyenv_steps_per_core=0):
     """Reference CPU path on `cores` processes (mirrors num_actors: the reference's only parallelism)."""
     ctx = mp.get_context("spawn")
-    per = [trees // cores + (1 if i < trees % cores else 0) for i in range(cores)]
-    per = [p for p in per if p > 0]
-    with ctx.Pool(len(per)) as pool:
-        t0 = time.perf_counter()
+    n_proc = max(1, min(cores, trees))
+    per = [trees // n_proc + (1 if i < trees % n_proc else 0) for i in range(n_proc)]
+    preset = 0 if game == "Hanabi-Full" else 1
+    with ctx.Pool(cores) as pool:
         res = pool.map(_ref_tree_worker, [(p, A, S, 100 + i, reps) for i, p in enumerate(per)])
-        wall = time.perf_counter() - t0
         wall = max(max(r[0] for r in res), 1e-9)
         sims_s = trees * (S - 1) * reps / wall
-        eres = pool.map(_ref_env_worker, [(env_steps_per_core, i) for i in range(len(per))])
-        env_s = env_steps_per_core * len(per) / max(r[0] for r in eres)
-    return dict(sims_per_s=sims_s, env_steps_per_s=env_s, kind=res[0][1], env_kind=eres[0][1], cores=len(per),
-                wall_s=wall)
+        eres = pool.map(_ref_env_worker, [(env_steps_per_core, i, preset) for i in range(cores)])
+        env_s = env_steps_per_core * cores / max(r[0] for r in eres)
+        py_s = None
+        if pyenv_steps_per_core:
+            pres = pool.map(_ref_pyenv_worker, [(pyenv_steps_per_core, i, game) for i in range(cores)])
+            if all(r is not None for r in pres):
+                py_s = pyenv_steps_per_core * cores / max(pres)
+    return dict(sims_per_s=sims_s, env_steps_per_s=env_s, pyenv_steps_per_s=py_s, kind=res[0][1], env_kind=eres[0][1],
+                cores=cores, tree_procs=n_proc, wall_s=wall)
 
 
-def reference_with_model(trees, A, S):
+def reference_with_model(trees, A, S, game="Hanabi-Full", obs_dim=785):
     """Informational: the loop of core/mcts.py:24-55 exactly as the reference runs it — its own cytree on the
     host, the PyTorch network on the GPU, Python-list marshalling, host hidden-state gather, H2D of the batch
     and D2H of the outputs EVERY simulation (one actor process).  Returns simulations/s or None."""
     try:
-        import importlib.util
         import torch
         if not torch.cuda.is_available():
             return None
-        ref_dir = os.path.join(ROOT, "oracle", "_ref")
-        so = [f for f in os.listdir(ref_dir) if f.startswith("cytree.") and f.endswith(".so")] if os.path.isdir(ref_dir) else []
-        if not so:
+        tree = _load_ref_cytree()
+        if tree is None:
             return None
-        spec = importlib.util.spec_from_file_location("cytree", os.path.join(ROOT, "oracle", "_ref", so[0]))
-        tree = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(tree)
-        from hanabizero_b200.model import MuZeroNetFull
+        from hanabizero_b200.model import MuZeroNet, MuZeroNetFull
         torch.manual_seed(0)
-        model = MuZeroNetFull(785 * 4, A).randomize_heads(seed=0).cuda().eval()
+        net = MuZeroNetFull if game == "Hanabi-Full" else MuZeroNet
+        model = net(obs_dim * 4, A).randomize_heads(seed=0).cuda().eval()
         rng = np.random.default_rng(0)
-        obs = torch.from_numpy((rng.random((trees, 785 * 4)) < 0.2).astype(np.float32)).cuda()
+        obs = torch.from_numpy((rng.random((trees, obs_dim * 4)) < 0.2).astype(np.float32)).cuda()
         best = None
         for rep in range(2):
             with torch.no_grad():
@@ -203,36 +277,42 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    A, S = 20, args.sims
-    trees = args.trees * args.gpus
+    wl = resolve_workload(args, max(args.gpus, 1))
+    A, S, trees = wl["A"], wl["sims"], wl["total"]
+    # a step = one search of the whole job's root batch on the host cores; small batches are repeated so that a
+    # step lasts long enough to time (the repeat count is part of the sample description)
+    reps = max(1, int(round(2e5 / max(trees * (S - 1), 1))))
     times = []
     out = None
     for i in range(args.warmup + args.steps):
-        out = cpu_reference(trees, A, S, cores, reps=1, env_steps_per_core=5000)
+        out = cpu_reference(trees, A, S, cores, reps=reps, env_steps_per_core=5000, game=wl["game"],
+                            pyenv_steps_per_core=300 if i == args.warmup + args.steps - 1 else 0)
         if i >= args.warmup:
             times.append(out)
     val = statistics.mean(t["sims_per_s"] for t in times)
     env = statistics.mean(t["env_steps_per_s"] for t in times)
-    sample = (f"{trees} Hanabi-Full trees x {S - 1} simulations per step split over {out['cores']} processes; "
-              "reference cytree driven like core/mcts.py with pre-generated network outputs (no model time); "
-              f"env: {5000 * out['cores']} steps of reference libhanabi (apply+deal+2x observe/encode), random legal play")
+    sample = (f"{trees} {wl['game']} trees x {S - 1} simulations (x{reps} repeats) per step split over {out['tree_procs']} "
+              "processes; reference cytree driven like core/mcts.py with pre-generated network outputs (no model time); "
+              f"env: {5000 * out['cores']} steps of reference libhanabi (apply+deal+2x observe/encode), random legal play; "
+              f"env_python_api: {300 * out['cores']} steps of the reference's HanabiEnv.step (rl_env.py) over {out['cores']} processes")
     line = {
         "impl": "reference", "metric": "mcts_simulations_per_sec", "value": val, "unit": "simulations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * trees * (S - 1) / val, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * trees * (S - 1) / val, "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Hanabi-Full 2p, {args.trees} trees/GPU x {S} simulations ({S - 1} executed)",
-                   "trees_total": trees, "actions": A},
+        "config": {"workload": f"{wl['name']}: {trees} trees in total ({wl['per_gpu']} per GPU x {args.gpus}), "
+                               f"{S - 1} simulations executed", "trees_total": trees, "actions": A, "simulations": S,
+                   "baseline_config": wl["config"]},
         "cpu_baseline": {"value": val, "unit": "simulations/s", "cores": out["cores"], "kind": out["kind"], "sample": sample},
         "e2e": {"value": val, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "env": {"metric": "hanabi_env_steps_per_sec", "value": env, "unit": "steps/s", "kind": out["env_kind"],
-                "cores": out["cores"]},
+                "cores": out["cores"], "python_api_steps_per_s": out["pyenv_steps_per_s"]},
         "gpu_launches": 0,
         "reference_with_model_on_gpu": {
-            "value": reference_with_model(min(args.trees, 1024), A, S), "unit": "simulations/s",
+            "value": reference_with_model(min(trees, 1024), A, S, wl["game"], wl["obs_dim"]), "unit": "simulations/s",
             "what": "informational: one reference actor, its own cytree on the host + the PyTorch network on cuda:0 with "
                     "per-simulation H2D/D2H and list marshalling exactly as core/mcts.py:24-55 does, "
-                    f"{min(args.trees, 1024)} trees x {S - 1} simulations"},
+                    f"{min(trees, 1024)} trees x {S - 1} simulations"},
     }
     print(json.dumps(line), flush=True)
 
@@ -281,18 +361,77 @@ class ClockSampler(threading.Thread):
 
 
 def ncu_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the
-    committed `ncu --set full` capture (profiles/); None if the summary is missing."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the newest
+    committed `ncu --set full` capture of that kernel under profiles/; (None, None) if there is none."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01c_ncu_full_k_search_step.csv")
-    try:
-        rows = list(csv.reader(open(path)))
-        hdr, units = rows[0], rows[1]
-        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if "1, 1" in r[ik]]
-        return sum(vals) / len(vals) if vals else None
-    except Exception:
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_k_search_step*.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:]
+                    if "k_search_step" in r[ik]]
+            if vals:
+                return sum(vals) / len(vals), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
+class SearchBench:
+    """Everything one rank needs to time searches of `n` trees: roots from real Hanabi positions, the model, the
+    device-resident step and the host-facing (end-to-end) steps."""
+
+    def __init__(self, torch, args, wl, n, rank, world, dev, model):
+        from hanabizero_b200 import cytree
+        from hanabizero_b200.dist import AsyncStatsGather
+        from hanabizero_b200.hanabi_env import HanabiVecEnv
+        from hanabizero_b200.mcts import MCTS, SearchConfig
+        self.torch, self.cytree, self.args, self.wl = torch, cytree, args, wl
+        self.n, self.rank, self.world, self.dev, self.model = n, rank, world, dev, model
+        A, S = wl["A"], wl["sims"]
+        self.A, self.S = A, S
+        self.cfg = SearchConfig(num_simulations=S, amp_type=args.amp)
+        # synthetic roots: real Hanabi positions (reset + 10 random legal steps) -> initial inference
+        self.env = HanabiVecEnv(n, wl["game"], np.arange(n) + rank * n, device=dev)
+        g, loc, legal = self.env.reset_all()
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        for _ in range(10):
+            acts = torch.multinomial(legal, 1, generator=gen).view(-1).int()
+            g, loc, legal, _, _, _ = self.env.step_all(acts, auto_reset=True)
+        self.env.check()
+        obs = (g if wl["mdp"] == "global" else loc).repeat(1, args.stack)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=args.amp == "torch_amp"):
+            _, root_logits, root_hidden = model.initial_inference_device(obs)
+        self.root_logits = root_logits.float().contiguous()
+        self.root_hidden = root_hidden.contiguous()
+        rng = np.random.default_rng(7 + rank)
+        self.noise = torch.from_numpy(rng.dirichlet([0.3] * A, n).astype(np.float32)).to(dev)
+        self.zeros_r = torch.zeros(n, device=dev)
+        self.legal = legal
+        self.legal_i = legal.int().contiguous()
+        self.gather = AsyncStatsGather(n, A, dev, depth=2) if world > 1 else None
+        self.mcts = MCTS(self.cfg)
+        self.holder = [None]
+        self.ticket = None
+
+    def search_step(self):
+        """Roots.prepare + run_multi + root statistics (+ the statistics all_gather, off the compute stream)."""
+        roots = self.cytree.Roots(self.n, self.A, self.S, device=self.dev)
+        roots.prepare(CONST["frac"], self.noise, self.zeros_r, self.root_logits, self.legal_i)
+        self.mcts.run_multi(roots, self.model, self.root_hidden, use_graph=not self.args.no_graph)
+        visits, values = roots.get_stats_tensors()
+        if self.gather is not None:
+            self.ticket = self.gather.submit(visits, values)
+        self.holder[0] = roots
+        return visits, values
+
+    def finish(self):
+        """All ranks' statistics of the last search (waits for the in-flight gather on the current stream)."""
+        if self.gather is not None and self.ticket is not None:
+            return self.gather.result(self.ticket)
         return None
 
 
@@ -300,10 +439,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from hanabizero_b200 import _lib, cytree
-    from hanabizero_b200.dist import gather_root_stats_equal
     from hanabizero_b200.hanabi_env import HanabiVecEnv
-    from hanabizero_b200.mcts import MCTS, SearchConfig
-    from hanabizero_b200.model import MuZeroNetFull
+    from hanabizero_b200.mcts import MCTS, SearchPipeline
+    from hanabizero_b200.model import MuZeroNet, MuZeroNetFull
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -316,81 +454,75 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
-    N, A, S, F = args.trees, 20, args.sims, F_HIDDEN
+    wl = resolve_workload(args, world)
+    N, A, S, F = wl["per_gpu"], wl["A"], wl["sims"], F_HIDDEN
     K, W = args.steps, max(args.warmup, 3)
-    cfg = SearchConfig(num_simulations=S, amp_type=args.amp)
     torch.manual_seed(0)
-    obs_dim = 785 if args.mdp == "global" else 660
-    model = MuZeroNetFull(obs_dim * args.stack, A).randomize_heads(seed=0).to(dev).eval()
-
-    # ---- synthetic roots: real Hanabi positions (reset + k random legal steps) -> initial inference ----
-    env = HanabiVecEnv(N, "Hanabi-Full", np.arange(N) + rank * N, device=dev)
-    g, loc, legal = env.reset_all()
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    for _ in range(10):
-        acts = torch.multinomial(legal, 1, generator=gen).view(-1).int()
-        g, loc, legal, _, _, _ = env.step_all(acts, auto_reset=True)
-    env.check()
-    obs = (g if args.mdp == "global" else loc).repeat(1, args.stack)
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16, enabled=args.amp == "torch_amp"):
-        _, root_logits, root_hidden = model.initial_inference_device(obs)
-    root_logits = root_logits.float().contiguous()
-    root_hidden = root_hidden.contiguous()
-    rng = np.random.default_rng(7 + rank)
-    noise = torch.from_numpy(rng.dirichlet([0.3] * A, N).astype(np.float32)).to(dev)
-    zeros_r = torch.zeros(N, device=dev)
-    legal_i = legal.int().contiguous()
-    packed = torch.empty(world * N, A + 1, dtype=torch.int32, device=dev) if world > 1 else None
-
-    mcts = MCTS(cfg)
-    launches_before, gemm_before = _lib.launch_count(), _lib.gemm_launch_count()
-
-    def search_step(roots_holder):
-        roots = cytree.Roots(N, A, S, device=dev)
-        roots.prepare(CONST["frac"], noise, zeros_r, root_logits, legal_i)
-        mcts.run_multi(roots, model, root_hidden, use_graph=not args.no_graph)
-        visits, values = roots.get_stats_tensors()
-        if world > 1:
-            visits, values = gather_root_stats_equal(visits, values, packed)
-        roots_holder[0] = roots
-        return visits, values
-
-    holder = [None]
-    search_step(holder)                       # eager search (also the launch census)
-    torch.cuda.synchronize()
-    launches_per_search = _lib.launch_count() - launches_before
-    gemm_per_search = _lib.gemm_launch_count() - gemm_before
-    for _ in range(W):
-        search_step(holder)
-    torch.cuda.synchronize()
+    net = MuZeroNetFull if wl["game"] == "Hanabi-Full" else MuZeroNet
+    model = net(wl["obs_dim"] * args.stack, A).randomize_heads(seed=0).to(dev).eval()
+    sb = SearchBench(torch, args, wl, N, rank, world, dev, model)
+    env, cfg, mcts = sb.env, sb.cfg, sb.mcts
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def time_searches(bench, steps, warm):
+        """CUDA-event time of `steps` searches of one SearchBench (barrier + synchronize on both sides, max over
+        ranks); the gather of the last search is inside the timed region."""
+        for _ in range(warm):
+            bench.search_step()
+        bench.finish()
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            visits, values = bench.search_step()
+        out = bench.finish()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)), visits, out
+
+    launches_before, gemm_before = _lib.launch_count(), _lib.gemm_launch_count()
+    sb.search_step()                       # eager search (also the launch census)
+    torch.cuda.synchronize()
+    launches_per_search = _lib.launch_count() - launches_before
+    gemm_per_search = _lib.gemm_launch_count() - gemm_before
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)   # let nvidia-smi attach before the timed regions
     # ---- timed region 1: device-resident search ------------------------------------------------
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        visits, values = search_step(holder)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t_ms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total = float(t_ms.item())
+    ms_total, visits, gathered = time_searches(sb, K, W)
     sims_total = world * N * (S - 1) * K
     value = sims_total / (ms_total * 1e-3)
-    assert int(visits[:N].sum().item()) == N * (S - 1), "search did not run the expected simulations"
+    assert int(visits.sum().item()) == N * (S - 1), "search did not run the expected simulations"
+    if gathered is not None:
+        assert gathered[0].shape[0] == world * N and torch.equal(gathered[0][rank * N:(rank + 1) * N], visits), \
+            "gathered root statistics do not contain this rank's shard"
 
-    # ---- timed region 2: end to end through the list/numpy drop-in API with pinned host buffers ------
+    # with more than one GPU: the same search with the config's tree count PER GPU (weak scaling), for the record
+    weak = None
+    if world > 1 and wl["scaling"] == "strong" and not args.quick:
+        wl_w = dict(wl, per_gpu=wl["total"], total=wl["total"] * world, scaling="weak")
+        sbw = SearchBench(torch, args, wl_w, wl_w["per_gpu"], rank, world, dev, model)
+        kw = max(K // 2, 3)
+        ms_w, _, _ = time_searches(sbw, kw, 3)
+        weak = {"value": wl_w["total"] * (S - 1) * kw / (ms_w * 1e-3), "unit": "simulations/s", "trees_per_gpu": wl_w["per_gpu"],
+                "trees_total": wl_w["total"], "ms_per_step": ms_w / kw, "steps": kw}
+        del sbw
+
+    # ---- timed region 2: end to end through the host-facing API with pinned host buffers ----------------
+    noise, root_logits, root_hidden, legal_i = sb.noise, sb.root_logits, sb.root_hidden, sb.legal_i
     h_noise, h_logits = noise.cpu().pin_memory(), root_logits.cpu().pin_memory()
     h_legal, h_hidden = legal_i.cpu().pin_memory(), root_hidden.cpu().pin_memory()
     h_reward = torch.zeros(N).pin_memory()
@@ -405,7 +537,7 @@ def run_ours(args):
         h_visits.copy_(v, non_blocking=True)
         h_values.copy_(val, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        holder[0] = roots
+        sb.holder[0] = roots
         return h_visits
 
     def timed_e2e(step_fn, finish=None, warm=2):
@@ -421,14 +553,10 @@ def run_ours(args):
             finish()
         e1.record()
         barrier()
-        t = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return sims_total / (float(t.item()) * 1e-3)
+        return sims_total / (max_over_ranks(max(e0.elapsed_time(e1), 0.0)) * 1e-3)
 
     e2e_serial = timed_e2e(e2e_step)
     # the same work through the double-buffered public API: the copies of neighbouring searches overlap the search
-    from hanabizero_b200.mcts import SearchPipeline
     pipe = SearchPipeline(mcts, model, N, A, depth=2, device=dev)
     h_out = [(torch.empty(N, A, dtype=torch.int32).pin_memory(), torch.empty(N).pin_memory()) for _ in range(2)]
     turn = [0]
@@ -444,276 +572,333 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in (h_noise, h_logits, h_legal, h_hidden, h_reward))
     d2h = h_visits.numel() * 4 + h_values.numel() * 4
 
-    # ---- timed region 3: Hanabi env steps (device-resident and e2e) -------------------------------
-    T = args.env_steps
-    acts_buf = torch.zeros(N, dtype=torch.int32, device=dev)
+    # ---- plan path vs nn.Module path: do the two ways of running the SAME network pick the same moves? -------
+    agreement = None
+    if rank == 0 and not args.quick and N * S <= 4096 * 50:
+        roots_m = cytree.Roots(N, A, S, device=dev)
+        roots_m.prepare(CONST["frac"], noise, sb.zeros_r, root_logits, legal_i)
+        MCTS(cfg, use_plan=False).run_multi(roots_m, model, root_hidden, use_graph=False)
+        vm, valm = roots_m.get_stats_tensors()
+        vp = h_visits.to(dev)
+        agreement = {"root_action_agreement": float((vm.argmax(1) == vp.argmax(1)).float().mean()),
+                     "visit_count_l1_per_tree": float((vm - vp).abs().sum(1).float().mean()),
+                     "root_value_max_abs_diff": float((valm - h_values.to(dev)).abs().max()),
+                     "what": "arg-max root action of the production path (BN-folded fp16 GEMM plan + fused tree step) vs the "
+                             "nn.Module path (PyTorch autocast kernels + generic tree calls) on the same roots and noise; the "
+                             "trees are bit-exact functions of the network outputs, the difference is network rounding"}
+        del roots_m
 
-    def env_pass(steps, host):
-        """host: None = device-resident; "f32" / "u8" = scalar-API style (actions come from the host, the
-        observation and the legal mask go back to the host every step) with float32 or byte observations."""
-        nonlocal legal
-        for _ in range(steps):
-            if host:
-                acts_buf.copy_(h_acts, non_blocking=True)
-            else:
-                acts_buf.copy_(torch.argmax(legal * torch.rand_like(legal), dim=1))
-            if host == "u8":
-                env.step_all(acts_buf, auto_reset=True, want_local=False, out_global=g8, out_legal=legal8)
-                h_obs8.copy_(g8_store, non_blocking=True)
-                h_leg8.copy_(legal8, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                h_acts.copy_(torch.from_numpy(np.argmax(h_leg8.numpy() * host_rand, axis=1).astype(np.int32)))
-                continue
-            gg, _, legal, r, d, s = env.step_all(acts_buf, auto_reset=True, want_local=False)
-            if host:
-                h_obs.copy_(gg, non_blocking=True)
-                h_leg.copy_(legal, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
-
-    gpad = (env.global_dim + 15) // 16 * 16
-    g8_store = torch.zeros(N, gpad, dtype=torch.uint8, device=dev)     # 16-byte-multiple rows: word stores
-    g8, legal8 = g8_store[:, :env.global_dim], torch.zeros(N, A, dtype=torch.uint8, device=dev)
-    h_obs = torch.empty(N, env.global_dim).pin_memory()
-    h_leg = torch.empty(N, A).pin_memory()
-    h_obs8 = torch.empty(N, gpad, dtype=torch.uint8).pin_memory()
-    h_leg8 = torch.empty(N, A, dtype=torch.uint8).pin_memory()
-    h_acts = torch.zeros(N, dtype=torch.int32).pin_memory()
-    host_rand = rng.random((N, A)).astype(np.float32) + 0.01
-
-    def host_pick():
-        h_leg.copy_(legal); torch.cuda.synchronize()
-        h_acts.copy_(torch.from_numpy(np.argmax(h_leg.numpy() * host_rand, axis=1).astype(np.int32)))
-
-    def timed_env(steps, host, warm):
-        if host:
-            host_pick()
-        env_pass(warm, host)
+    env_obj, selfplay_obj = None, None
+    if not args.quick:
+        env_obj = bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, rank, world, dev)
+        # ---- whole self-play moves, device-resident ----
+        from hanabizero_b200.selfplay import SelfPlayEngine
+        eng = SelfPlayEngine(N, wl["game"], model, cfg, seeds=np.arange(N) + 7 * N * (rank + 1), mdp=wl["mdp"],
+                             stack=args.stack, device=dev)
+        eng.reset()
+        for _ in range(3):
+            eng.step()
         barrier()
         e0.record()
-        env_pass(steps, host)
+        n_moves = 5
+        for _ in range(n_moves):
+            eng.step()
         e1.record()
         barrier()
-        if host == "u8":       # the float legal mask of the device path is stale after byte steps
-            env.observe()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * N * steps / (float(t.item()) * 1e-3)
-
-    T_host = max(T // 4, 10)
-    # device-resident: ten steps (action pick + fused step/auto-reset/observe launch) per CUDA graph, replayed — the
-    # Python loop around five tiny launches per step would otherwise be what is timed
-    env_pass(20, None)
-    torch.cuda.synchronize()
-    per_graph = 10
-    env_graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(env_graph):
-        env_pass(per_graph, None)
-    legal = env.legal
-    reps = max(T // per_graph, 1)
-    env_graph.replay()
-    barrier()
-    e0.record()
-    for _ in range(reps):
-        env_graph.replay()
-    e1.record()
-    barrier()
-    t_env = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t_env, op=dist.ReduceOp.MAX)
-    env_value = world * N * reps * per_graph / (float(t_env.item()) * 1e-3)
-    T = reps * per_graph
-    legal = env.legal
-    env_e2e_f32 = timed_env(T_host, "f32", 5)
-    legal = env.legal
-    env_e2e = timed_env(T_host, "u8", 5)
-    legal = env.legal
-    env.check()
-    # ---- timed region 4 (informational): whole self-play moves, device-resident (SURVEY §8f N1/N2 rows) ----
-    from hanabizero_b200.selfplay import SelfPlayEngine
-    eng = SelfPlayEngine(N, "Hanabi-Full", model, cfg, seeds=np.arange(N) + 7 * N * (rank + 1), mdp=args.mdp,
-                         stack=args.stack, device=dev)
-    eng.reset()
-    for _ in range(3):
-        eng.step()
-    barrier()
-    e0.record()
-    n_moves = 5
-    for _ in range(n_moves):
-        eng.step()
-    e1.record()
-    barrier()
-    sp_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(sp_ms, op=dist.ReduceOp.MAX)
-    eng.env.check()
-    selfplay_moves = world * N * n_moves / (float(sp_ms.item()) * 1e-3)
+        sp_ms = max_over_ranks(e0.elapsed_time(e1))
+        eng.env.check()
+        selfplay_moves = world * N * n_moves / (sp_ms * 1e-3)
+        selfplay_obj = {"metric": "selfplay_moves_per_sec", "value": selfplay_moves, "unit": "moves/s",
+                        "what": "frame stack -> representation+prediction -> Roots.prepare(Dirichlet) -> run_multi -> "
+                                "select_action -> env step with auto-reset, all on the device (SelfPlayEngine.step)",
+                        "simulations_per_sec": selfplay_moves * (S - 1),
+                        "fraction_of_search_only": selfplay_moves * (S - 1) / value}
+        del eng
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant tree kernel (fused backprop+traverse+gather), timed live ----------
-    roof = None
-    env_roof = None
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # the production launch: hz_trees_search_step (decode + expand + backprop + min/max + traverse +
-        # hand-off) on synthetic network outputs, alone on the stream, L2 flushed before every launch
-        plan = model.recurrent_plan(torch.float16 if args.amp == "torch_amp" else torch.float32)
-        ch = plan.chain(N)
-        eb = ch.x0.element_size()
-        ch.out.copy_(torch.randn_like(ch.out.float()).to(ch.out.dtype))
-        ch.state.copy_(torch.rand_like(ch.state.float()).to(ch.state.dtype))
-        roots = cytree.Roots(N, A, S, device=dev)
-        roots.prepare(CONST["frac"], noise, zeros_r, root_logits, legal_i)
-        mm = cytree.MinMaxStatsList(N); mm.set_delta(CONST["delta"])
-        pool = torch.rand(S, N, F, device=dev).to(ch.x0.dtype)
-        io = _lib.SearchIO()
-        io.value_logits, io.ld_value = ch.value_logits.data_ptr(), ch.value_logits.stride(0)
-        io.reward_logits, io.ld_reward = ch.reward_logits.data_ptr(), ch.reward_logits.stride(0)
-        io.policy_logits, io.ld_policy = ch.policy_logits.data_ptr(), ch.policy_logits.stride(0)
-        io.next_state, io.ld_state = ch.state.data_ptr(), ch.state.stride(0)
-        io.support, io.support_width, io.support_delta = plan.support.data_ptr(), plan.n_support, plan.net.support_delta
-        io.elem_bytes, io.sanitize_nan = eb, 1
-        io.pool, io.state_cols = pool.data_ptr(), F
-        io.out_batch, io.ld_batch, io.onehot_cols = ch.x0.data_ptr(), ch.x0.stride(0), plan.OH
-        io.out_ix, io.out_action = None, None
-        io.minmax, io.value_delta_max = mm.tensor(dev).data_ptr(), CONST["delta"]
-        io.discount, io.pb_c_base, io.pb_c_init = CONST["discount"], CONST["pb_c_base"], CONST["pb_c_init"]
-        st = torch.cuda.current_stream().cuda_stream
-        ref = _lib.C.byref(io)
-        _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        depth_sum, depth_max = 0.0, []
-        gen_out = torch.Generator(device=dev).manual_seed(99)
-        outs = [torch.randn(ch.out.shape, device=dev, generator=gen_out).to(ch.out.dtype) for _ in range(8)]
-        for x in range(1, S - 1):
-            ch.out.copy_(outs[x % 8])   # fresh synthetic network outputs per simulation (realistic tree depths)
-            flush.fill_(x & 1)  # evict L2: every launch starts cold, like inside a search whose working set exceeds L2
-            evs[x][0].record()
-            _lib.check(lib.hz_trees_search_step(roots.handle, st, x, 1, ref))
-            evs[x][1].record()
-            pl = roots.export(1)["path_len"].float()
-            depth_sum += float(pl.mean().item()) - 1.0
-            depth_max.append(int(pl.max().item()) - 1)
-        torch.cuda.synchronize()
-        durs = [evs[x][0].elapsed_time(evs[x][1]) * 1e-3 for x in range(1, S - 1)]
-        # the same launches back to back inside a CUDA graph, no flush (what the search loop sees: 270 MB of
-        # tree + pool per search is larger than L2, but the hot nodes of a tree stay L2-resident between sims)
-        roots.prepare(CONST["frac"], noise, zeros_r, root_logits, legal_i)
-        mm.clear()
-        _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
-        torch.cuda.synchronize()
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            st_c = torch.cuda.current_stream().cuda_stream
-            for x in range(1, S - 1):
-                ch.out.copy_(outs[x % 8])
-                _lib.check(lib.hz_trees_search_step(roots.handle, st_c, x, 1, ref))
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        gr.replay()
-        w1.record()
-        torch.cuda.synchronize()
-        _lib.check(lib.hz_trees_set_progress(roots.handle, S - 2))
-        gc = torch.cuda.CUDAGraph()      # the same graph without the tree launches: the copies' own cost
-        with torch.cuda.graph(gc):
-            for x in range(1, S - 1):
-                ch.out.copy_(outs[x % 8])
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        gc.replay()
-        c1.record()
-        torch.cuda.synchronize()
-        warm_us = (w0.elapsed_time(w1) - c0.elapsed_time(c1)) * 1e3 / (S - 2)
-        n_l = len(durs)
-        D = depth_sum / n_l
-        s_mean = statistics.mean(range(1, S - 1))
-        # SURVEY §8d per-simulation bytes (tree part with the hidden row in the model dtype) + what this fused
-        # launch additionally replaces: reading both support-logit rows and copying the new state into the pool
-        per_tree = b_sim(A, D, s_mean, F * eb / 4.0) + 2 * plan.n_support * eb + 2 * F * eb
-        bytes_launch = N * per_tree
-        achieved = bytes_launch / statistics.mean(durs) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_search_step<half,backprop,traverse> (hz_trees_search_step)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_per_launch(),
-                "peak_source": peak_src, "launch_us": 1e6 * statistics.mean(durs), "launch_us_in_graph_no_flush": warm_us,
-                "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_tree": per_tree,
-                "mean_depth": D, "l2": "flushed before every timed launch (256 MiB write)",
-                "per_sim_us_flushed": [round(1e6 * d, 1) for d in durs[::6]], "max_depth": depth_max[::6]}
-        # env kernel
-        evs2 = []
-        for _ in range(30):
-            flush.fill_(1)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            acts_buf.copy_(torch.argmax(legal * torch.rand_like(legal), dim=1))
-            a0.record()
-            _, _, legal, _, _, _ = env.step_all(acts_buf, auto_reset=True, want_local=False)
-            a1.record()
-            evs2.append((a0, a1))
-        torch.cuda.synchronize()
-        d2 = statistics.mean(a.elapsed_time(b) for a, b in evs2) * 1e-3
-        env_roof = {"bound": "hbm", "kernel": "k_env<step,observe>", "achieved": N * B_ENV_STEP / d2 / 1e9, "peak": peak,
-                    "unit": "GB/s", "frac": N * B_ENV_STEP / d2 / 1e9 / peak, "traffic": None, "launch_us": d2 * 1e6}
+    roof = tree_roofline(torch, args, wl, sb, model, lib) if rank == 0 else None
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        one = cpu_reference(min(N, 1024), A, S, 1, reps=4, env_steps_per_core=100000)
-        allc = cpu_reference(N, A, S, cores, reps=6, env_steps_per_core=100000)
+        trees_c = wl["total"]
+        reps_all = max(1, int(round(1.2e6 / max(trees_c * (S - 1), 1))))
+        one = cpu_reference(min(trees_c, 1024), A, S, 1, reps=max(1, reps_all // 8), env_steps_per_core=100000, game=wl["game"],
+                            pyenv_steps_per_core=2000)
+        allc = cpu_reference(trees_c, A, S, cores, reps=reps_all, env_steps_per_core=100000, game=wl["game"],
+                             pyenv_steps_per_core=1000)
         cpu = {"value": allc["sims_per_s"], "unit": "simulations/s", "cores": allc["cores"], "kind": allc["kind"],
                "value_1core": one["sims_per_s"],
                "env_steps_per_s": allc["env_steps_per_s"], "env_steps_per_s_1core": one["env_steps_per_s"],
+               "env_python_api_steps_per_s": allc["pyenv_steps_per_s"],
+               "env_python_api_steps_per_s_1core": one["pyenv_steps_per_s"],
                "env_kind": allc["env_kind"],
-               "sample": (f"{N} Hanabi-Full trees x {S - 1} simulations x 6 over {allc['cores']} processes (and "
-                          f"{min(N, 1024)} trees x 4 on 1 core): reference cytree driven like core/mcts.py with pre-generated "
-                          "network outputs, no model time; env: 100000 steps/core of reference libhanabi in C++ "
-                          "(about 20 core-seconds in total)")}
+               "sample": (f"{trees_c} {wl['game']} trees x {S - 1} simulations x {reps_all} over {allc['tree_procs']} processes "
+                          f"(and {min(trees_c, 1024)} trees x {max(1, reps_all // 8)} on 1 core): reference cytree driven like "
+                          "core/mcts.py with pre-generated network outputs, no model time; env: 100000 steps/core of reference "
+                          "libhanabi in C++; env_python_api: the reference's own HanabiEnv.step (rl_env.py over pyhanabi.py + "
+                          "cffi), 1000 steps/core (2000 on 1 core) — what its callers pay per step")}
 
     if rank == 0:
+        nodes_mb = N * (S + 1) * A * 16 / 1e6
+        pool_mb = N * S * F * (2 if args.amp == "torch_amp" else 4) / 1e6
         line = {
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"Hanabi-Full 2p {args.mdp} {'MDP' if args.mdp == 'global' else 'POMDP'}, {N} trees/GPU x {S} simulations ({S - 1} executed, "
-                                   "as core/mcts.py:25-26), MuZeroNetFull random-init with re-drawn heads",
-                       "trees_per_gpu": N, "trees_total": world * N, "actions": A, "simulations": S, "stack": args.stack,
-                       "model_amp": args.amp, "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
-                       "l2": "working set (tree nodes 67 MB + hidden pool >200 MB per search) exceeds the 126 MB L2"},
+            "config": {"workload": f"{wl['name']}: {wl['total']} trees in total, {N} per GPU x {world} GPU(s) ({wl['scaling']} "
+                                   f"scaling), {S - 1} simulations executed per search (core/mcts.py:25-26), "
+                                   f"{'MuZeroNetFull' if wl['game'] == 'Hanabi-Full' else 'MuZeroNet'} random-init with re-drawn heads",
+                       "baseline_config": wl["config"], "trees_per_gpu": N, "trees_total": wl["total"], "actions": A,
+                       "simulations": S, "stack": args.stack, "mdp": wl["mdp"], "model_amp": args.amp,
+                       "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
+                       "l2": f"per search the tree nodes ({nodes_mb:.0f} MB) + hidden pool ({pool_mb:.0f} MB) per GPU; the roofline "
+                             "launches are timed with L2 flushed (256 MiB write) before each one"},
             "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "SearchPipeline.submit/wait (hanabizero_b200/mcts.py): pinned host inputs in, root statistics out, "
                            "every search; two searches in flight so the copies overlap the neighbouring search",
                     "serial": {"value": e2e_serial, "api": "Roots.prepare + MCTS.run_multi + get_stats on host tensors, one "
                                                            "search at a time, a stream synchronise per search"}},
+            "us_per_simulation": 1e3 * ms_total / K / (S - 1),
             "gpu_launches": int(launches_per_search * K),
             "gpu_launches_per_search": int(launches_per_search),
             "library_gemm_launches_per_search": int(gemm_per_search),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "env": {"metric": "hanabi_env_steps_per_sec", "value": env_value, "unit": "steps/s",
-                    "e2e": {"value": env_e2e, "unit": "steps/s", "h2d_bytes_per_step": 4 * N,
-                            "d2h_bytes_per_step": N * (gpad + A), "obs_dtype": "u8",
-                            "what": "actions from pinned host memory in, global observation + legal mask out as 0/1 "
-                                    "bytes (the encoder's own value type, hz_envs_step_observe_u8), host picks the next "
-                                    "action; one sync per step",
-                            "f32": {"value": env_e2e_f32, "d2h_bytes_per_step": 4 * N * (env.global_dim + A)}},
-                    "games_per_gpu": N, "steps_timed": T, "includes": "on-device random legal action pick (3 torch kernels) + "
-                    "fused step/auto-reset/observe kernel, ten steps per CUDA graph", "roofline": env_roof},
-            "selfplay": {"metric": "selfplay_moves_per_sec", "value": selfplay_moves, "unit": "moves/s",
-                         "what": "frame stack -> representation+prediction -> Roots.prepare(Dirichlet) -> run_multi -> "
-                                 "select_action -> env step with auto-reset, all on the device (SelfPlayEngine.step)",
-                         "simulations_per_sec": selfplay_moves * (S - 1)},
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "weak": weak, "plan_vs_module": agreement,
+            "env": env_obj, "selfplay": selfplay_obj,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, rank, world, dev):
+    """Hanabi env steps/s: device-resident (CUDA graph of ten steps), host-facing (bit-packed observations through the
+    double-buffered EnvPipeline; byte and float32 variants for comparison), the scalar drop-in HanabiEnv.step, the
+    kernel's roofline line, and a saturated run with many more games than trees."""
+    from hanabizero_b200.hanabi_env import EnvPipeline, HanabiEnv, HanabiVecEnv
+    N, A, T = env.num_games, env.num_actions, args.env_steps
+    legal = sb.legal
+    rng = np.random.default_rng(11 + rank)
+    acts_buf = torch.zeros(N, dtype=torch.int32, device=dev)
+
+    def device_pass(e, steps, lg, buf):
+        for _ in range(steps):
+            buf.copy_(torch.argmax(lg * torch.rand_like(lg), dim=1))
+            _, _, lg, _, _, _ = e.step_all(buf, auto_reset=True, want_local=False)
+        return lg
+
+    def timed_graph(e, lg, buf, total_steps, per_graph=10):
+        lg = device_pass(e, 20, lg, buf)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            device_pass(e, per_graph, lg, buf)
+        reps = max(total_steps // per_graph, 1)
+        gr.replay()
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            gr.replay()
+        e1.record()
+        barrier()
+        return world * e.num_games * reps * per_graph / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3), reps * per_graph
+
+    env_value, steps_timed = timed_graph(env, legal, acts_buf, T)
+    env.check()
+
+    # saturated: many more games per GPU than the search has trees (the env kernel alone is latency-bound at 4096)
+    sat = {}
+    for games in (16384, 65536):
+        big = HanabiVecEnv(games, wl["game"], np.arange(games) + 1000003 * (rank + 1), device=dev)
+        _, _, lg = big.reset_all()
+        v, _ = timed_graph(big, lg, torch.zeros(games, dtype=torch.int32, device=dev), max(T // 2, 20))
+        big.check()
+        sat[str(games)] = v
+        del big
+
+    # host-facing: actions from pinned host memory in, observation + legal mask out, every step
+    T_host = max(T // 4, 10)
+    host_rand = rng.random((N, A)).astype(np.float32) + 0.01
+
+    def timed_pipeline(fmt):
+        pipe = EnvPipeline(env, fmt=fmt, depth=2)
+        h_acts = [torch.zeros(N, dtype=torch.int32).pin_memory() for _ in range(2)]
+        tk = pipe.observe_now()
+        for step in range(5 + T_host):
+            if step == 5:
+                barrier()
+                e0.record()
+            obs, leg = pipe.wait(tk)                      # pinned host views of the previous step's result
+            a = h_acts[step % 2]
+            a.copy_(torch.from_numpy(np.argmax(leg.numpy()[:, :A] * host_rand, axis=1).astype(np.int32)))
+            tk = pipe.step(a)
+        pipe.wait(tk)
+        e1.record()
+        barrier()
+        v = world * N * T_host / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        return v, pipe.d2h_bytes_per_step
+
+    e2e_bits, d2h_bits = timed_pipeline("bits")
+    e2e_u8, d2h_u8 = timed_pipeline("u8")
+    e2e_f32, d2h_f32 = timed_pipeline("f32")
+    env.observe()
+    env.check()
+
+    # the scalar drop-in (rl_env.py API, one game): what a caller that keeps the reference's loop gets
+    scalar = None
+    if rank == 0:
+        one = HanabiEnv({"hanabi_name": wl["game"], "seed": 1})
+        _, _, lg1 = one.reset()
+        n_sc = 300
+        t0 = time.perf_counter()
+        for _ in range(n_sc):
+            _, _, _, done, _, lg1 = one.step(int(rng.choice(np.flatnonzero(np.asarray(lg1)))))
+            if done:
+                _, _, lg1 = one.reset()
+        scalar = n_sc / (time.perf_counter() - t0)
+
+    # roofline of the env kernel: one launch at a time, L2 flushed, float32 observations (what the network eats)
+    env_roof = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        evs = []
+        lg = env.legal
+        for _ in range(30):
+            flush.fill_(1)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            acts_buf.copy_(torch.argmax(lg * torch.rand_like(lg), dim=1))
+            a0.record()
+            _, _, lg, _, _, _ = env.step_all(acts_buf, auto_reset=True, want_local=False)
+            a1.record()
+            evs.append((a0, a1))
+        torch.cuda.synchronize()
+        d2 = statistics.mean(a.elapsed_time(b) for a, b in evs) * 1e-3
+        by = N * b_env_step(env.global_dim, A, 4)
+        env_roof = {"bound": "hbm", "kernel": "k_env<step,observe> (float32 observations)", "achieved": by / d2 / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": by / d2 / 1e9 / peak, "traffic": None, "launch_us": d2 * 1e6,
+                    "algorithmic_bytes_per_game": b_env_step(env.global_dim, A, 4), "peak_source": peak_src}
+    return {"metric": "hanabi_env_steps_per_sec", "value": env_value, "unit": "steps/s",
+            "games_per_gpu": N, "steps_timed": steps_timed,
+            "includes": "on-device random legal action pick (3 torch kernels) + fused step/auto-reset/observe kernel, ten "
+                        "steps per CUDA graph",
+            "saturated": {"what": "the same device-resident loop with more games per GPU than the search has trees",
+                          "steps_per_s_by_games_per_gpu": sat},
+            "e2e": {"value": e2e_bits, "unit": "steps/s", "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": d2h_bits,
+                    "obs_format": "bits",
+                    "what": "EnvPipeline (hanabizero_b200/hanabi_env.py): actions from pinned host memory in, the global "
+                            "observation as a bit string (785 bits -> 100 bytes per game, hz_envs_step_observe_bits) + legal "
+                            "mask + reward/done/score out to pinned host memory every step, the host picks the next action "
+                            "from the returned mask; two steps in flight on two streams",
+                    "u8": {"value": e2e_u8, "d2h_bytes_per_step": d2h_u8},
+                    "f32": {"value": e2e_f32, "d2h_bytes_per_step": d2h_f32}},
+            "scalar_dropin_steps_per_s": scalar,
+            "roofline": env_roof}
+
+
+def measured_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if "hbm_gbs" in peaks:
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def tree_roofline(torch, args, wl, sb, model, lib):
+    """Roofline of the dominant kernel of this repository — the fused tree step (hz_trees_search_step: decode +
+    expand + back-propagate + min/max + traverse + hand-off) — timed live: one launch per simulation on synthetic
+    network outputs, alone on the stream, L2 flushed before every launch; and the same launches back to back inside
+    a CUDA graph (what the search loop sees)."""
+    from hanabizero_b200 import _lib, cytree
+    N, A, S, F, dev = sb.n, sb.A, sb.S, F_HIDDEN, sb.dev
+    peak, peak_src = measured_peak()
+    plan = model.recurrent_plan(torch.float16 if args.amp == "torch_amp" else torch.float32)
+    ch = plan.chain(N)
+    eb = ch.x0.element_size()
+    ch.out.copy_(torch.randn_like(ch.out.float()).to(ch.out.dtype))
+    roots = cytree.Roots(N, A, S, device=dev)
+    roots.prepare(CONST["frac"], sb.noise, sb.zeros_r, sb.root_logits, sb.legal_i)
+    mm = cytree.MinMaxStatsList(N); mm.set_delta(CONST["delta"])
+    pool = torch.rand(S, N, F, device=dev).to(ch.x0.dtype)
+    io = _lib.SearchIO()
+    io.value_logits, io.ld_value = ch.value_logits.data_ptr(), ch.value_logits.stride(0)
+    io.reward_logits, io.ld_reward = ch.reward_logits.data_ptr(), ch.reward_logits.stride(0)
+    io.policy_logits, io.ld_policy = ch.policy_logits.data_ptr(), ch.policy_logits.stride(0)
+    io.next_state, io.ld_state = None, 0     # as in the search loop: the dynamics GEMM writes pool[x] itself
+    io.support, io.support_width, io.support_delta = plan.support.data_ptr(), plan.n_support, plan.net.support_delta
+    io.elem_bytes, io.sanitize_nan = eb, 1
+    io.pool, io.state_cols = pool.data_ptr(), F
+    io.out_batch, io.ld_batch, io.onehot_cols = ch.x0.data_ptr(), ch.x0.stride(0), plan.OH
+    io.out_ix, io.out_action = None, None
+    io.minmax, io.value_delta_max = mm.tensor(dev).data_ptr(), CONST["delta"]
+    io.discount, io.pb_c_base, io.pb_c_init = CONST["discount"], CONST["pb_c_base"], CONST["pb_c_init"]
+    st = torch.cuda.current_stream().cuda_stream
+    ref = _lib.C.byref(io)
+    _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(S)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    depth_sum, depth_max = 0.0, []
+    gen_out = torch.Generator(device=dev).manual_seed(99)
+    outs = [torch.randn(ch.out.shape, device=dev, generator=gen_out).to(ch.out.dtype) for _ in range(8)]
+    for x in range(1, S - 1):
+        ch.out.copy_(outs[x % 8])   # fresh synthetic network outputs per simulation (realistic tree depths)
+        flush.fill_(x & 1)          # evict L2: every launch starts cold
+        evs[x][0].record()
+        _lib.check(lib.hz_trees_search_step(roots.handle, st, x, 1, ref))
+        evs[x][1].record()
+        pl = roots.export(1)["path_len"].float()
+        depth_sum += float(pl.mean().item()) - 1.0
+        depth_max.append(int(pl.max().item()) - 1)
+    torch.cuda.synchronize()
+    durs = [evs[x][0].elapsed_time(evs[x][1]) * 1e-3 for x in range(1, S - 1)]
+    # the same launches back to back inside a CUDA graph, no flush
+    roots.prepare(CONST["frac"], sb.noise, sb.zeros_r, sb.root_logits, sb.legal_i)
+    mm.clear()
+    _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        st_c = torch.cuda.current_stream().cuda_stream
+        for x in range(1, S - 1):
+            ch.out.copy_(outs[x % 8])
+            _lib.check(lib.hz_trees_search_step(roots.handle, st_c, x, 1, ref))
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    gr.replay()
+    w1.record()
+    torch.cuda.synchronize()
+    _lib.check(lib.hz_trees_set_progress(roots.handle, S - 2))
+    gc = torch.cuda.CUDAGraph()      # the same graph without the tree launches: the copies' own cost
+    with torch.cuda.graph(gc):
+        for x in range(1, S - 1):
+            ch.out.copy_(outs[x % 8])
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    gc.replay()
+    c1.record()
+    torch.cuda.synchronize()
+    warm_us = (w0.elapsed_time(w1) - c0.elapsed_time(c1)) * 1e3 / (S - 2)
+    D = depth_sum / len(durs)
+    s_mean = statistics.mean(range(1, S - 1))
+    # SURVEY §8d B_sim (tree part + the hidden-row gather in the pool's dtype) + the two support-logit rows and the
+    # policy row this launch decodes.  Nothing else: the state -> pool copy of round 1 is gone from the kernel.
+    per_tree = b_sim(A, D, s_mean, F * eb / 4.0) + (2 * plan.n_support + A) * eb
+    bytes_launch = N * per_tree
+    achieved = bytes_launch / statistics.mean(durs) / 1e9
+    traffic, traffic_src = ncu_traffic_per_launch()
+    return {"bound": "hbm", "kernel": "k_search_step<half,backprop,traverse> (hz_trees_search_step)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src, "launch_us": 1e6 * statistics.mean(durs), "launch_us_in_graph_no_flush": warm_us,
+            "frac_in_graph_no_flush": bytes_launch / (warm_us * 1e-6) / 1e9 / peak,
+            "algorithmic_bytes_per_launch": bytes_launch, "algorithmic_bytes_per_tree": per_tree,
+            "mean_depth": D, "l2": "flushed before every timed launch (256 MiB write)",
+            "per_sim_us_flushed": [round(1e6 * d, 1) for d in durs[::6]], "max_depth": depth_max[::6]}
 
 
 if __name__ == "__main__":

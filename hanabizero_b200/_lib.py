@@ -44,16 +44,16 @@ SIGNATURES = {
     "hz_gemm_plan_create": (_i, [C.POINTER(_vp), _i, _i, _vp, _i]),
     "hz_gemm_plan_destroy": (_i, [_vp]),
     "hz_gemm_plan_steps": (_i, [_vp]),
-    "hz_gemm_plan_fused": (_i, [_vp]),
+    "hz_gemm_plan_set_operand": (_i, [_vp, _i, _i, _vp]),
     "hz_gemm_launch_count": (_i64, []),
     "hz_gemm_plan_run": (_i, [_vp, _vp, _i, _i]),
     "hz_trees_set_progress": (_i, [_vp, _i]),
+    "hz_trees_set_tie_break": (_i, [_vp, _i, C.c_uint64, _i]),
     "hz_trees_root_stats": (_i, [_vp, _vp, _vp, _vp]),
     "hz_trees_trajectories": (_i, [_vp, _vp, _vp, _i]),
     "hz_trees_export": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hz_gather_hidden": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i]),
     "hz_support_decode": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i64, _f]),
-    "hz_bias_act": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i]),
     "hz_select_action": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "hz_stack_push": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i]),
     "hz_traj_begin": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
@@ -83,7 +83,7 @@ class SearchIO(C.Structure):
                 ("sanitize_nan", C.c_int32), ("pool", _vp), ("state_cols", C.c_int32), ("out_batch", _vp),
                 ("ld_batch", _i64), ("onehot_cols", C.c_int32), ("out_ix", _vp), ("out_action", _vp),
                 ("minmax", _vp), ("value_delta_max", _f), ("discount", _f), ("pb_c_base", C.c_int32),
-                ("pb_c_init", _f)]
+                ("pb_c_init", _f), ("programmatic_launch", C.c_int32)]
 
 
 class TrajView(C.Structure):

@@ -15,7 +15,6 @@
 
 #include <vector>
 
-#include "hz_chain.h"
 #include "hz_common.cuh"
 
 namespace hz {
@@ -51,7 +50,6 @@ struct hz_gemm_plan {
   size_t ws_bytes = 0;
   bool autotune = false;
   std::vector<LtStep> steps;
-  hz::ChainExec* fused = nullptr;   // persistent one-launch executor (hz_chain.cu), fp16 plans
 };
 
 #define HZ_LT(call)                                                         \
@@ -184,11 +182,7 @@ int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz
   p->device = device;
   p->elem_bytes = elem_bytes;
   p->ws_bytes = 32u << 20;
-  {
-    // opt-in: timing the heuristic's top candidates changed nothing measurable on B200 (34.9 vs 34.0 us per chain)
-    const char* env = getenv("HZ_GEMM_AUTOTUNE");
-    p->autotune = env && env[0] == '1';
-  }
+  p->autotune = false;   // timing the heuristic's candidates changed nothing measurable on B200 (34.9 vs 34.0 us per chain)
   if (cublasLtCreate(&p->lt) != CUBLAS_STATUS_SUCCESS) { delete p; set_error("cublasLtCreate failed"); return HZ_ERR_CUDA; }
   cudaError_t e = cudaMalloc(&p->workspace, p->ws_bytes);
   if (e != cudaSuccess) { cublasLtDestroy(p->lt); delete p; return fail_cuda(e, "hz_gemm_plan_create: workspace"); }
@@ -200,12 +194,6 @@ int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz
       return rc;
     }
   }
-  if (chain_supported(steps, n_steps, elem_bytes, nullptr)) {
-    if (int rc = chain_create(&p->fused, device, steps, n_steps)) {
-      hz_gemm_plan_destroy(p);
-      return rc;
-    }
-  }
   *out = p;
   return HZ_OK;
 }
@@ -213,7 +201,6 @@ int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz
 int hz_gemm_plan_destroy(hz_gemm_plan* p) {
   if (!p) return HZ_OK;
   DeviceGuard dg(p->device);
-  chain_destroy(p->fused);
   for (auto& st : p->steps) free_step(st);
   if (p->workspace) cudaFree(p->workspace);
   if (p->lt) cublasLtDestroy(p->lt);
@@ -225,11 +212,21 @@ int64_t hz_gemm_launch_count(void) { return g_gemm_launches.load(); }
 
 int hz_gemm_plan_steps(const hz_gemm_plan* p) { return p ? (int)p->steps.size() : 0; }
 
-int hz_gemm_plan_fused(const hz_gemm_plan* p) { return p && p->fused ? chain_grid(p->fused) : 0; }
-
-// debug (not in include/hzb200.h): per-CTA, per-step globaltimer stamps of the last fused run (HZ_CHAIN_TRACE=1)
-int hz_debug_chain_trace(const hz_gemm_plan* p, unsigned long long* out, int64_t count) {
-  return p ? chain_trace(p->fused, out, (size_t)count) : 0;
+int hz_gemm_plan_set_operand(hz_gemm_plan* p, int step, int which, void* ptr) {
+  if (!p || step < 0 || step >= (int)p->steps.size() || which < 0 || which > 2 || !ptr) {
+    set_error("hz_gemm_plan_set_operand: bad argument");
+    return HZ_ERR_ARG;
+  }
+  if ((uintptr_t)ptr & 255) {   // the algorithms were chosen for 256-byte aligned operands
+    set_error("hz_gemm_plan_set_operand: operand must be 256-byte aligned");
+    return HZ_ERR_ARG;
+  }
+  hz_gemm_step& s = p->steps[step].s;
+  if (which == 1 && !s.c) { set_error("hz_gemm_plan_set_operand: step %d has no residual operand", step); return HZ_ERR_ARG; }
+  if (which == 0) s.a = ptr;
+  else if (which == 1) s.c = ptr;
+  else s.d = ptr;
+  return HZ_OK;
 }
 
 int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count) {
@@ -238,7 +235,6 @@ int hz_gemm_plan_run(hz_gemm_plan* p, void* stream, int first, int count) {
     return HZ_ERR_ARG;
   }
   DeviceGuard dg(p->device);
-  if (p->fused && first == 0 && count == (int)p->steps.size()) return chain_run(p->fused, (cudaStream_t)stream);
   const float alpha = 1.0f;
   for (int i = first; i < first + count; ++i) {
     LtStep& st = p->steps[i];

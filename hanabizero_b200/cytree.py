@@ -16,13 +16,20 @@ device; results are Python lists like the reference's, or CUDA tensors with `as_
 the `*_tensor` accessors so that nothing has to leave the device.  All tree state lives in HBM
 inside a `hz_trees` handle (include/hzb200.h); there is no CPU implementation behind this module.
 
-Deviations from the reference, all unreachable from its own callers:
-  * ties between children within 1e-6 of the best score are broken by the first index
-    (the reference draws rand() % ties after reseeding from the clock, cnode.cpp:367-369,409-411);
+Deviations from the reference:
+  * ties between children within 1e-6 of the best score: the reference draws rand() % ties after reseeding libc's
+    generator from the clock (cnode.cpp:367-369,409-411), which no one can reproduce.  Default here: the first element
+    of the reference's tie list (= its rand() == 0 build, the contract of the bit-exact parity tests).  With
+    `Roots.set_tie_break("random", seed)` the pick is uniform over the same tie list from a counter-based generator —
+    use it whenever ties are systematic, e.g. with the reference's zero-initialised output heads, where every
+    non-root node is an A-way tie and first-index would always descend action 0;
   * hidden_state_index_x passed to multi_back_propagate must be 1, 2, 3, ... in order, which is
     what core/mcts.py:52-55 passes; anything else raises instead of silently mis-indexing;
   * sizes are checked (the reference has no bounds checks: wrong sizes are undefined behaviour).
 """
+import collections
+import weakref
+
 import numpy as np
 import torch
 
@@ -31,8 +38,43 @@ from ._lib import check, ptr
 
 FLOAT_MAX = 1000000.0  # core/ctree/cminimax.h:7
 
-_free_handles = {}  # (device, num, actions, cap) -> [hz_trees*]: reused so that CUDA graphs captured
-                    # against a handle stay valid when the caller builds a new Roots every move
+# (device, num, actions, cap) -> [(hz_trees*, release event)]: handles are reused so that CUDA graphs captured against
+# a handle stay valid when the caller builds a new Roots every move (as the reference's callers do).  The cache is
+# bounded: beyond MAX_FREE_SHAPES distinct shapes (or MAX_FREE_PER_SHAPE idle handles of one shape) the least
+# recently used handles are destroyed (hz_trees_destroy) and everything keyed on them is told to forget them.
+_free_handles = collections.OrderedDict()
+MAX_FREE_SHAPES = 6
+MAX_FREE_PER_SHAPE = 4
+_destroy_listeners = []   # weak references to callables(handle_value) — MCTS drops workspaces/graphs of a dead handle
+
+
+def on_handle_destroyed(fn):
+    _destroy_listeners.append(weakref.WeakMethod(fn) if hasattr(fn, "__self__") else weakref.ref(fn))
+
+
+def _destroy_handle(lib, h):
+    for ref in list(_destroy_listeners):
+        fn = ref()
+        if fn is None:
+            _destroy_listeners.remove(ref)
+        else:
+            fn(h.value)
+    lib.hz_trees_destroy(h)
+
+
+def trim_free_handles(keep_shapes=None, keep_per_shape=None):
+    """Destroy idle tree batches beyond the cache bounds (all of them with keep_shapes=0)."""
+    keep_shapes = MAX_FREE_SHAPES if keep_shapes is None else keep_shapes
+    keep_per_shape = MAX_FREE_PER_SHAPE if keep_per_shape is None else keep_per_shape
+    lib = _lib.load()
+    while len(_free_handles) > keep_shapes:
+        _, idle = _free_handles.popitem(last=False)
+        for h, _ in idle:
+            _destroy_handle(lib, h)
+    for idle in _free_handles.values():
+        while len(idle) > keep_per_shape:
+            h, _ = idle.pop(0)
+            _destroy_handle(lib, h)
 
 
 def _device_index(device):
@@ -114,7 +156,11 @@ class Roots:
         self._lib = _lib.load()
         free = _free_handles.get(self._key)
         if free:
-            self._h = free.pop()
+            _free_handles.move_to_end(self._key)
+            self._h, released = free.pop()
+            # whatever stream used the handle last must be done with it before this stream touches it
+            torch.cuda.current_stream(self.device).wait_event(released)
+            check(self._lib.hz_trees_set_tie_break(self._h, 0, 0, 0))
         else:
             h = _lib.C.c_void_p()
             check(self._lib.hz_trees_create(_lib.C.byref(h), self.device_index, self.root_num,
@@ -123,12 +169,25 @@ class Roots:
         self._prepared = False
         self._keep = None
 
+    def set_tie_break(self, mode="first", seed=0, tree_offset=0):
+        """cselect_child's tie rule (cnode.cpp:367-369): "first" = element 0 of the tie list (the reference built with
+        rand() == 0; default), "random" = uniform over the list, drawn from a counter-based generator keyed by
+        (seed, tree_offset + tree, simulation, depth).  `tree_offset` = global index of this batch's first tree."""
+        modes = {"first": 0, "random": 1}
+        if mode not in modes:
+            raise ValueError("tie-break mode must be 'first' or 'random'")
+        check(self._lib.hz_trees_set_tie_break(self.handle, modes[mode], int(seed) & (2 ** 64 - 1), int(tree_offset)))
+
     # -- lifetime ------------------------------------------------------------------------------
     def release(self):
         """Return the HBM buffers to the per-shape free list (done automatically on __del__)."""
         if getattr(self, "_h", None) is not None:
-            _free_handles.setdefault(self._key, []).append(self._h)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            _free_handles.setdefault(self._key, []).append((self._h, ev))
+            _free_handles.move_to_end(self._key)
             self._h = None
+            trim_free_handles()
 
     def __del__(self):
         try:

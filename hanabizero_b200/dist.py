@@ -49,3 +49,57 @@ def gather_root_stats_equal(visits, values, out_packed, group=None):
     packed[:, a] = values.view(torch.int32)
     dist.all_gather_into_tensor(out_packed, packed, group=group)
     return out_packed[:, :a], out_packed[:, a].view(torch.float32)
+
+
+class AsyncStatsGather:
+    """The search's one collective, taken off the compute stream: `submit` packs this rank's root statistics and
+    issues the all_gather on a side stream that waits only for the statistics kernel, so the next search's
+    `Roots.prepare` and simulations run while NCCL moves the 84 B per tree; `result` makes the current stream wait
+    for a ticket.  `depth` gathers can be in flight (one packed/out buffer pair each).  Equal shard sizes."""
+
+    def __init__(self, n_local, actions, device, depth=2, group=None):
+        self.group, self.depth = group, int(depth)
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.n, self.a, self.device = int(n_local), int(actions), device
+        self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.slots = [dict(packed=torch.empty(self.n, self.a + 1, dtype=torch.int32, device=device),
+                           out=torch.empty(self.world * self.n, self.a + 1, dtype=torch.int32, device=device),
+                           done=torch.cuda.Event() if self.stream is not None else None, used=False)
+                      for _ in range(self.depth)]
+        self._next = 0
+
+    def submit(self, visits, values):
+        i = self._next
+        self._next = (i + 1) % self.depth
+        s = self.slots[i]
+        if self.stream is None:       # gloo / CPU tensors: nothing to overlap with
+            s["packed"][:, :self.a] = visits
+            s["packed"][:, self.a] = values.contiguous().view(torch.int32)
+            if self.world > 1:
+                dist.all_gather_into_tensor(s["out"], s["packed"], group=self.group)
+            else:
+                s["out"].copy_(s["packed"])
+            return i
+        cur = torch.cuda.current_stream(self.device)
+        if s["used"]:
+            cur.wait_event(s["done"])            # the slot's previous gather has been consumed in stream order
+        self.stream.wait_stream(cur)             # after the statistics kernel (and nothing later)
+        with torch.cuda.stream(self.stream):
+            s["packed"][:, :self.a] = visits
+            s["packed"][:, self.a] = values.view(torch.int32)
+            if self.world > 1:
+                dist.all_gather_into_tensor(s["out"], s["packed"], group=self.group)
+            else:
+                s["out"].copy_(s["packed"])
+            s["done"].record(self.stream)
+        visits.record_stream(self.stream)
+        values.record_stream(self.stream)
+        s["used"] = True
+        return i
+
+    def result(self, ticket):
+        """(visits int32 [world*n, A], values float32 [world*n]) of a ticket; the current stream waits for it."""
+        s = self.slots[ticket]
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_event(s["done"])
+        return s["out"][:, :self.a], s["out"][:, self.a].view(torch.float32)

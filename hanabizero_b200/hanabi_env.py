@@ -36,8 +36,8 @@ class HanabiVecEnv:
             raise ValueError("Unknown environment {}".format(hanabi_name))  # rl_env.py:133
         self.num_games = int(num_games)
         self.hanabi_name = hanabi_name
-        self.device_index = (torch.cuda.current_device() if device is None
-                             else (torch.device(device).index or 0))
+        from .cytree import _device_index   # device="cuda" (no index) means the CURRENT device, not cuda:0
+        self.device_index = _device_index(device)
         self.device = torch.device("cuda", self.device_index)
         if seeds is None:
             seeds = np.zeros(self.num_games, np.int32)  # seed=None -> 0 (rl_env.py:106-109)

@@ -18,6 +18,7 @@ device-resident path.  A model with only the reference's `recurrent_inference` (
 NetworkOutput) still works through the same kernels, paying that model's own host hops.
 """
 import contextlib
+import weakref
 
 import numpy as np
 import torch
@@ -47,8 +48,10 @@ class _Workspace:
     """Static device buffers of one (tree handle, model, shape): hidden-state pool [S, N, F], the
     gathered batch handed to the model, the min/max statistics, and the captured graph."""
 
-    def __init__(self, roots, sims, feature, dtype):
+    def __init__(self, roots, model, sims, feature, dtype):
         n, dev = roots.root_num, roots.device
+        self.model_ref = weakref.ref(model)   # id(model) can be recycled: a hit must be for the same live object
+        self.chain = None                     # the BoundChain a captured graph points into (kept alive with it)
         self.pool = torch.empty(sims, n, feature, dtype=dtype, device=dev)
         self.hidden = torch.empty(n, feature, dtype=dtype, device=dev)
         self.action64 = torch.zeros(n, 1, dtype=torch.int64, device=dev)
@@ -67,6 +70,12 @@ class MCTS(object):
         self.config = config
         self.use_plan = use_plan
         self._ws = {}
+        cytree.on_handle_destroyed(self._forget_handle)
+
+    def _forget_handle(self, handle_value):
+        """A cached tree batch was destroyed: graphs captured over its buffers must never be replayed."""
+        for key in [k for k in self._ws if k[0] == handle_value]:
+            del self._ws[key]
 
     # ---------------------------------------------------------------------------------------------
     def _autocast(self):
@@ -85,6 +94,8 @@ class MCTS(object):
         sims = int(self.config.num_simulations)
         key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"), self.use_plan)
         ws = self._ws.get(key)
+        if ws is not None and ws.model_ref() is not model:
+            ws = None   # a different model object that happens to live at a recycled address
         if ws is None:
             n, dev = roots.root_num, roots.device
             feature = int(hidden_state_roots.shape[-1])
@@ -99,7 +110,7 @@ class MCTS(object):
                 dtype = torch.float32
             if len(self._ws) >= self.max_cached_workspaces:
                 self._ws.pop(next(iter(self._ws)))
-            ws = self._ws[key] = _Workspace(roots, sims, feature, dtype)
+            ws = self._ws[key] = _Workspace(roots, model, sims, feature, dtype)
         return ws
 
     def _simulate(self, roots, model, ws):
@@ -143,12 +154,12 @@ class MCTS(object):
         mm.clear()
         if sims < 2:
             return
-        ch = plan.chain(roots.root_num)
+        ch = ws.chain = plan.chain(roots.root_num)   # referenced by the workspace: outlives an eviction from the plan's cache
         io = _lib.SearchIO()
         io.value_logits, io.ld_value = ptr(ch.value_logits), ch.value_logits.stride(0)
         io.reward_logits, io.ld_reward = ptr(ch.reward_logits), ch.reward_logits.stride(0)
         io.policy_logits, io.ld_policy = ptr(ch.policy_logits), ch.policy_logits.stride(0)
-        io.next_state, io.ld_state = ptr(ch.state), ch.state.stride(0)
+        io.next_state, io.ld_state = None, 0      # the dynamics GEMM writes pool[x] itself (BoundChain.bind_state)
         io.support, io.support_width, io.support_delta = ptr(plan.support), plan.n_support, plan.net.support_delta
         io.elem_bytes, io.sanitize_nan = ch.x0.element_size(), 1
         io.pool, io.state_cols = ptr(ws.pool), plan.F
@@ -159,6 +170,7 @@ class MCTS(object):
         ref = _lib.C.byref(io)
         check(lib.hz_trees_search_step(h, st, 0, 1, ref))
         for x in range(1, sims):
+            ch.bind_state(ws.pool[x])
             ch.run(st)
             check(lib.hz_trees_search_step(h, st, x, 1 if x < sims - 1 else 0, ref))
 

@@ -97,6 +97,18 @@ class BoundChain:
         arr = (GemmStep * self.n_steps)(*steps)
         self._h = C.c_void_p()
         check(plan.lib.hz_gemm_plan_create(C.byref(self._h), dev.index, self.x0.element_size(), arr, self.n_steps))
+        self._state_ptr = self.state.data_ptr()   # where step 2 writes / step 3 reads the new hidden state
+
+    def bind_state(self, state):
+        """Make the dynamics network write its output (and the heads read it) at `state` ([n, F], plan dtype,
+        contiguous) instead of the chain's own buffer: the search loop passes pool[x], so no copy is needed."""
+        p = state.data_ptr()
+        if p != self._state_ptr:
+            if state.shape != self.state.shape or state.dtype != self.state.dtype or not state.is_contiguous():
+                raise ValueError("bind_state: shape/dtype/layout must match the chain's state buffer")
+            check(self.plan.lib.hz_gemm_plan_set_operand(self._h, 2, 2, p))   # fc3: D
+            check(self.plan.lib.hz_gemm_plan_set_operand(self._h, 3, 0, p))   # heads' first layer: A
+            self._state_ptr = p
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -138,21 +150,28 @@ class RecurrentPlan:
         self.n_support = net._value_support.numel()
         if net._reward_support.numel() != self.n_support:
             raise ValueError("value and reward supports must have the same size")
-        self.P3 = _round_up(self.n_support, 16)   # 16: one tcgen05 column tile (hz_chain.cu)
+        self.P3 = _round_up(self.n_support, 16)   # 32-byte aligned logit rows (vector loads in the decode)
         self.support = net._value_support.detach().float().contiguous()
         self._sig, self._w, self._chains = None, {}, {}
         self.refresh(force=True)
 
     # -- weights ---------------------------------------------------------------------------------------
     def _signature(self):
-        """Version counters of every parameter / buffer: in-place updates (optimizer steps, load_state_dict,
-        BN statistics) bump tensor._version.  Walking the module costs ~200 us, reading the counters of a cached
-        tensor list ~12 us, so the list is re-enumerated only every 64th call (that is when a parameter that was
-        re-assigned rather than updated in place is noticed)."""
-        self._sig_calls = getattr(self, "_sig_calls", 0) + 1
-        if getattr(self, "_tensors", None) is None or self._sig_calls % 64 == 0:
-            self._tensors = list(self.net.parameters()) + list(self.net.buffers())
-        return tuple(t._version for t in self._tensors) + tuple(t.data_ptr() for t in self._tensors[:2])
+        """Identity (data_ptr) and version counter of every parameter / buffer: in-place updates (optimizer steps,
+        load_state_dict, BN statistics) bump tensor._version, re-assignment (.half(), .to(), a new Parameter) changes
+        the tensor object.  The modules of a network are fixed after construction, so the list of modules is cached
+        and only their _parameters / _buffers dicts (where a re-assigned tensor shows up) are read per call."""
+        if getattr(self, "_modules_cache", None) is None:
+            self._modules_cache = list(self.net.modules())
+        sig = []
+        for m in self._modules_cache:
+            for t in m._parameters.values():
+                if t is not None:
+                    sig.append((t.data_ptr(), t._version))
+            for t in m._buffers.values():
+                if t is not None:
+                    sig.append((t.data_ptr(), t._version))
+        return tuple(sig)
 
     def _set(self, name, value):
         value = value.to(self.dtype).contiguous()
@@ -219,6 +238,7 @@ class RecurrentPlan:
         ch.x0[:, :self.F].copy_(hidden)
         ch.x0[:, self.F:].zero_()
         ch.x0[:, self.F:].scatter_(1, action.reshape(-1, 1), 1.0)
+        ch.bind_state(ch.state)
         ch.run(st)
         out_state.copy_(ch.state)
         dec = torch.empty(2 * n, dtype=torch.float32, device=self.device)

@@ -103,9 +103,10 @@ typedef struct hz_search_io {
   const void* value_logits;   int64_t ld_value;    /* [N][support_width] */
   const void* reward_logits;  int64_t ld_reward;   /* [N][support_width] */
   const void* policy_logits;  int64_t ld_policy;   /* [N][A] */
-  const void* next_state;     int64_t ld_state;    /* [N][state_cols] */
+  const void* next_state;     int64_t ld_state;    /* [N][state_cols], or NULL when the network wrote the new
+                                                    * hidden state straight into pool[x] (no copy in the kernel) */
   const float* support;       /* dev float[support_width] */
-  int32_t support_width;
+  int32_t support_width;      /* <= 256 */
   float support_delta;
   int32_t elem_bytes;
   int32_t sanitize_nan;       /* zero NaN policy logits (core/mcts.py:48-49) */
@@ -123,6 +124,10 @@ typedef struct hz_search_io {
   float discount;
   int32_t pb_c_base;
   float pb_c_init;
+  /* != 0: launch with programmatic stream serialization — the kernel fetches its tree state while the preceding
+   * kernel of the stream drains and synchronises on it before reading the network outputs.  The caller guarantees
+   * that the preceding kernel is not the previous tree step (there is at least one network kernel in between). */
+  int32_t programmatic_launch;
 } hz_search_io;
 int hz_trees_search_step(hz_trees* t, void* stream, int x, int do_traverse, const hz_search_io* io);
 
@@ -130,6 +135,16 @@ int hz_trees_search_step(hz_trees* t, void* stream, int x, int do_traverse, cons
  * (number of completed back-propagations since prepare) must be restored by hand: a replay runs
  * the kernels but not the host code.  expansions in [0, capacity]. */
 int hz_trees_set_progress(hz_trees* t, int expansions);
+
+/* Tie rule of cselect_child (cnode.cpp:346-374).  The reference draws rand() % ties over the children whose score is
+ * within 1e-6 of the best (after srand(gettimeofday) per traverse, cnode.cpp:409-411).  mode 0 (default, the parity
+ * contract with the rand() == 0 build of the reference): the first element of that list.  mode 1: a uniform draw
+ * from a counter-based generator keyed by (seed, tree_offset + tree index, simulations completed, depth) — the same
+ * tie LIST as the reference, a reproducible draw instead of the clock-seeded libc stream.  tree_offset is the global
+ * index of this batch's tree 0, so a root batch sharded over ranks draws exactly what the unsharded batch draws.
+ * Takes effect at the next hz_trees_prepare (which stores the rule in device memory, so a captured CUDA graph of the
+ * simulation loop follows the rule of the search it is replayed for); pass a fresh seed per search. */
+int hz_trees_set_tie_break(hz_trees* t, int mode, uint64_t seed, int tree_offset);
 
 /* CRoots::get_distributions / get_values (cnode.cpp:276-292): out_visits int32[N][A] (dev),
  * out_values float[N] (dev). */
@@ -216,13 +231,6 @@ int hz_envs_dump(hz_envs* e, void* stream, int32_t* out);
  * NaN -> 0.  out: dev float[rows]. */
 int hz_support_decode(void* stream, const void* logits, int elem_bytes, const float* support,
                       float* out, int rows, int width, int64_t ld, float delta);
-/* GEMM epilogue: out[r][c] = act(x[r][c] + bias[c] + residual[r][c] + table[idx[r]][c]); bias,
- * residual and table (+ int64 idx[rows]) are optional (NULL); relu != 0 applies max(.,0).
- * All matrices dev, element type by elem_bytes (4 float / 2 half), row strides in elements. */
-int hz_bias_act(void* stream, void* out, int64_t ld_out, const void* x, int64_t ld_x, const void* bias,
-                const void* residual, int64_t ld_res, const void* table, const int64_t* idx,
-                int rows, int cols, int relu, int elem_bytes);
-
 /* ------------------------------------------------------------------------------------------
  * "Next" rows: the hops between a search and the next env step.
  * ------------------------------------------------------------------------------------------ */
@@ -287,7 +295,8 @@ int hz_visit_policy(void* stream, const int32_t* visits, const uint8_t* mask, in
 
 /* A fixed chain of nn.Linear-shaped GEMMs executed with cuBLASLt, one launch each:
  *   D[m][n] = act( A[m][k] . W[n][k]^T + bias[n] + C[m][n] ),  all row-major, strided batches allowed.
- * Pointers are captured at creation (static buffers: the chain is CUDA-graph friendly). */
+ * Pointers are captured at creation (static buffers: the chain is CUDA-graph friendly); hz_gemm_plan_set_operand
+ * re-points single operands. */
 typedef struct hz_gemm_step {
   const void* a;    int64_t lda; int64_t stride_a;     /* activations */
   const void* w;    int64_t ldw; int64_t stride_w;     /* weights in nn.Linear layout [n][k] */
@@ -300,10 +309,10 @@ typedef struct hz_gemm_plan hz_gemm_plan;
 int hz_gemm_plan_create(hz_gemm_plan** out, int device, int elem_bytes, const hz_gemm_step* steps, int n_steps); /* sync */
 int hz_gemm_plan_destroy(hz_gemm_plan* p);                                                                     /* sync */
 int hz_gemm_plan_steps(const hz_gemm_plan* p);
-/* > 0 if a whole-plan run (first = 0, count = all) executes as ONE persistent tcgen05/TMA kernel of this library
- * (fp16 plans; value = its grid size) instead of one cuBLASLt launch per step; 0 otherwise.  HZ_FUSED_CHAIN=0 in the
- * environment keeps every plan on cuBLASLt. */
-int hz_gemm_plan_fused(const hz_gemm_plan* p);
+/* Re-point one operand of one step (which: 0 = A, 1 = C, 2 = D) at another buffer of the same shape and leading
+ * dimension, 256-byte aligned.  Takes effect for the following hz_gemm_plan_run calls (and is what a CUDA graph
+ * captures): the search loop makes the dynamics network write each new hidden state straight into pool[x]. */
+int hz_gemm_plan_set_operand(hz_gemm_plan* p, int step, int which, void* ptr);
 /* cuBLASLt launches issued through hz_gemm_plan_run in this process (library GEMMs, counted apart from
  * hz_launch_count, which counts this library's own kernels) */
 int64_t hz_gemm_launch_count(void);

@@ -66,6 +66,13 @@ class TreeEngine:
             self._f("free")(self.h)
             self.h = None
 
+    def set_tie(self, mode, seed=0, tree_offset=0):
+        """Tie rule (C restatement only): 0 = first of the tie list, 1 = counter-based uniform draw (hz::tie_hash)."""
+        fn = self._f("set_tie")
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int]
+        fn.restype = None
+        fn(self.h, int(mode), int(seed) & (2 ** 64 - 1), int(tree_offset))
+
     def prepare(self, frac, noises, rewards, logits, masks):
         nz = None if noises is None else np.ascontiguousarray(noises, np.float32)
         self._f("prepare")(self.h, frac, None if nz is None else nz.ctypes.data,

@@ -22,7 +22,7 @@ io = _lib.SearchIO()
 io.value_logits, io.ld_value = ch.value_logits.data_ptr(), ch.value_logits.stride(0)
 io.reward_logits, io.ld_reward = ch.reward_logits.data_ptr(), ch.reward_logits.stride(0)
 io.policy_logits, io.ld_policy = ch.policy_logits.data_ptr(), ch.policy_logits.stride(0)
-io.next_state, io.ld_state = ch.state.data_ptr(), ch.state.stride(0)
+io.next_state, io.ld_state = None, 0
 io.support, io.support_width, io.support_delta = plan.support.data_ptr(), plan.n_support, 1.0
 io.elem_bytes, io.sanitize_nan = 2, 1
 io.pool, io.state_cols = pool.data_ptr(), F
@@ -35,10 +35,9 @@ lib.hz_debug_set_trace.argtypes = [ctypes.c_void_p]
 _lib.check(lib.hz_debug_set_trace(trace.data_ptr()))
 _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
 gen = torch.Generator(device=dev).manual_seed(1)
-names = ["prologue+decode", "softmax+expand", "pathload+chain+write", "q patch+minmax", "traverse", "gather"]
+names = ["prologue+decode", "softmax+expand", "stage wait+backprop", "minmax", "traverse", "gather"]
 for x in range(1, S - 1):
     ch.out.copy_(torch.randn(ch.out.shape, device=dev, generator=gen).half())
-    ch.state.copy_(torch.rand(ch.state.shape, device=dev, generator=gen).half())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); _lib.check(lib.hz_trees_search_step(roots.handle, st, x, 1, ref)); e1.record()
@@ -52,7 +51,7 @@ for x in range(1, S - 1):
               f"per-warp total cycles mean {tot.mean():.0f} max {tot.max():.0f}")
         for k, nm in enumerate(names):
             print(f"    {nm:24s} mean {d[:, k].mean():8.0f}  p50 {np.median(d[:, k]):8.0f}  max {d[:, k].max():8.0f}")
-        for a, b, nm in ((0, 8, "issue prologue loads"), (8, 9, "wait for all loads"), (9, 10, "decode value"), (10, 11, "decode reward"), (11, 1, "store state row")):
+        for a, b, nm in ((0, 8, "issue staging + loads"), (8, 1, "decode value+reward")):
             dd = tr[:, b] - tr[:, a]
             print(f"      {nm:24s} mean {dd.mean():8.0f}  p50 {np.median(dd):8.0f}  max {dd.max():8.0f}")
         lv = d[:, 4] / np.maximum(depth, 1)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hanabizero_b200.dist import gather_root_stats, shard_range
+from hanabizero_b200.dist import AsyncStatsGather, gather_root_stats, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -30,6 +30,14 @@ def _worker(rank, world, port, total, A, ragged, out_q):
     lo, hi = shard_range(total, rank, world)
     v, val = gather_root_stats(torch.from_numpy(visits_all[lo:hi]), torch.from_numpy(values_all[lo:hi]))
     ok = bool((v.numpy() == visits_all).all() and (val.numpy().view(np.uint32) == values_all.view(np.uint32)).all())
+    if not ragged:   # the overlapped gather of the timed path (equal shards): two tickets in flight, results in order
+        ag = AsyncStatsGather(hi - lo, A, torch.device("cpu"), depth=2)
+        t0 = ag.submit(torch.from_numpy(visits_all[lo:hi]), torch.from_numpy(values_all[lo:hi]))
+        t1 = ag.submit(torch.from_numpy(visits_all[lo:hi] + 1), torch.from_numpy(values_all[lo:hi] * 2))
+        v0, val0 = ag.result(t0)
+        v1, val1 = ag.result(t1)
+        ok = ok and bool((v0.numpy() == visits_all).all() and (val0.numpy() == values_all).all()
+                         and (v1.numpy() == visits_all + 1).all() and (val1.numpy() == values_all * 2).all())
     out_q.put((rank, ok, tuple(v.shape)))
     dist.barrier()
     dist.destroy_process_group()

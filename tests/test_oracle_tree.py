@@ -74,3 +74,27 @@ def test_nan_and_extreme_inputs_match_reference():
             e.backprop(s + 1, CONST["discount"], d["sim_reward"][s], d["sim_value"][s], d["sim_logits"][s])
     for x, y in zip(o.stats(), r.stats()):
         assert bits_equal(x, y)
+
+
+def test_random_tie_mode_is_uniform_like_the_stock_reference():
+    """Tie mode 1 of the oracle (the counter-based draw the CUDA path uses) against the reference's stock build
+    (rand() % ties, clock-seeded): with the reference's zero-initialised heads every select is an A-way tie, so the
+    first action of a search is uniform over the actions for both — and never 'always action 0'."""
+    from helpers import tree_inputs
+    N, A, S = 4000, 20, 3
+    d = tree_inputs(N, A, S, 5)
+    for k in ("logits", "sim_logits", "sim_value", "sim_reward", "reward"):
+        d[k][:] = 0.0
+    d["mask"][:] = 1
+    counts = {}
+    engines = {"oracle": L.oracle_tree(N, A, S)}
+    engines["oracle"].set_tie(1, 2024, 0)
+    if L.have_ref():
+        engines["reference"] = L.ref_tree(N, A, S, deterministic=False)
+    for name, e in engines.items():
+        e.prepare(0.25, None, d["reward"], d["logits"], d["mask"])
+        la = e.traverse(19652, 1.25, 0.999)[2]
+        counts[name] = np.bincount(la, minlength=A)
+    for name, c in counts.items():
+        chi2 = ((c - N / A) ** 2 / (N / A)).sum()
+        assert chi2 < 60.0, f"{name}: first actions not uniform over {A}-way ties (chi2 {chi2:.1f}, 19 dof): {c}"

@@ -231,3 +231,46 @@ def test_errors_are_loud():
     cytree.multi_traverse(roots, 19652, 1.25, 0.999, mm, res)
     with pytest.raises(HzError):
         cytree.multi_back_propagate(3, 0.999, [0.0] * 4, [0.0] * 4, np.zeros((4, 20)), mm, res)  # x out of order
+
+
+def test_random_tie_break_generic_calls_match_oracle_on_degenerate_ties():
+    """The reference's stock initialisation zeroes the output heads: uniform priors, zero values -> every select is
+    an A-way tie.  Tie mode "random" must walk the same trees as the oracle running the same generator,
+    and must not always descend action 0."""
+    from gpu_adapters import GpuTreeEngine
+    from oracle import loader as L
+    N, A, S = 64, 20, 40
+    d = tree_inputs(N, A, S, 3)
+    for k in ("logits", "sim_logits", "sim_value", "sim_reward", "reward"):
+        d[k][:] = 0.0
+    d["mask"][:] = 1
+    gpu, cpu = GpuTreeEngine(N, A, S), L.oracle_tree(N, A, S)
+    gpu.roots.set_tie_break("random", 99, 7)
+    cpu.set_tie(1, 99, 7)
+    for e in (gpu, cpu):
+        e.prepare(CONST["frac"], None, d["reward"], d["logits"], d["mask"])
+    first_actions = []
+    for s in range(S - 1):
+        a = gpu.traverse(CONST["pb_c_base"], CONST["pb_c_init"], CONST["discount"])
+        b = cpu.traverse(CONST["pb_c_base"], CONST["pb_c_init"], CONST["discount"])
+        for x, y in zip(a, b):
+            assert (x == y).all(), f"simulation {s}"
+        first_actions.append(a[2].copy())
+        for e in (gpu, cpu):
+            e.backprop(s + 1, CONST["discount"], d["sim_reward"][s], d["sim_value"][s], d["sim_logits"][s])
+    assert (gpu.stats()[0] == cpu.stats()[0]).all()
+    assert len(np.unique(first_actions[0])) > A // 2        # the first pick is spread over the actions
+    # a shard of the batch with tree_offset draws exactly what the full batch draws for those trees
+    lo, hi = 24, 56
+    shard = GpuTreeEngine(hi - lo, A, S)
+    shard.roots.set_tie_break("random", 99, 7 + lo)
+    shard.prepare(CONST["frac"], None, d["reward"][lo:hi], d["logits"][lo:hi], d["mask"][lo:hi])
+    for s in range(S - 1):
+        a = shard.traverse(CONST["pb_c_base"], CONST["pb_c_init"], CONST["discount"])
+        assert (a[2] == first_actions[s][lo:hi]).all(), f"shard diverges at simulation {s}"
+        shard.backprop(s + 1, CONST["discount"], d["sim_reward"][s][lo:hi], d["sim_value"][s][lo:hi], d["sim_logits"][s][lo:hi])
+    assert (shard.stats()[0] == gpu.stats()[0][lo:hi]).all()
+    # default mode: element 0 of the tie list, i.e. action 0 at the first select of every tree
+    gpu0 = GpuTreeEngine(N, A, S)
+    gpu0.prepare(CONST["frac"], None, d["reward"], d["logits"], d["mask"])
+    assert (gpu0.traverse(CONST["pb_c_base"], CONST["pb_c_init"], CONST["discount"])[2] == 0).all()
