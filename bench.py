@@ -719,32 +719,50 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
         del big
 
     # host-facing: actions from pinned host memory in, observation + legal mask out, every step
-    T_host = max(T // 4, 10)
-    host_rand = rng.random((N, A)).astype(np.float32) + 0.01
+    T_host = max(T // 2, 20)
+
+    # two independent half-batches: while the host reads one half's result and picks its actions, the other half's
+    # copies and kernel are in flight
+    G = 2 if N >= 2 else 1
+    n_g = N // G
+    halves = [HanabiVecEnv(n_g, wl["game"], np.arange(n_g) + 500009 * (rank * G + gi + 1), device=dev) for gi in range(G)]
+    for h in halves:
+        h.reset_all(observe=False)
+    # host policy: a uniformly random legal move per game from the returned legal mask (hz_host_random_legal, a few
+    # nanoseconds per game in C; numpy needs ~15 vectorised passes = more than the whole device step)
+    rows_tmp = [torch.zeros(n_g, halves[0].bits_words, dtype=torch.int32) for _ in range(G)]
 
     def timed_pipeline(fmt):
-        pipe = EnvPipeline(env, fmt=fmt, depth=2)
-        h_acts = [torch.zeros(N, dtype=torch.int32).pin_memory() for _ in range(2)]
-        tk = pipe.observe_now()
+        pipe = EnvPipeline(halves, fmt=fmt)
+        h_acts = [torch.zeros(n_g, dtype=torch.int32).pin_memory() for _ in range(G)]
+        shifts = np.arange(A, dtype=np.uint32)
+        for gi in range(G):
+            pipe.observe_now(gi)
         for step in range(5 + T_host):
             if step == 5:
                 barrier()
                 e0.record()
-            obs, leg = pipe.wait(tk)                      # pinned host views of the previous step's result
-            a = h_acts[step % 2]
-            a.copy_(torch.from_numpy(np.argmax(leg.numpy()[:, :A] * host_rand, axis=1).astype(np.int32)))
-            tk = pipe.step(a)
-        pipe.wait(tk)
+            for gi in range(G):
+                obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
+                if fmt == "bits":
+                    rows = obs
+                else:                                           # 0/1 rows -> the same mask word
+                    rows = rows_tmp[gi]
+                    rows[:, -4] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
+                halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
+                pipe.step(gi, h_acts[gi])
+        pipe.drain()
         e1.record()
         barrier()
-        v = world * N * T_host / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+        v = world * n_g * G * T_host / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         return v, pipe.d2h_bytes_per_step
 
     e2e_bits, d2h_bits = timed_pipeline("bits")
     e2e_u8, d2h_u8 = timed_pipeline("u8")
     e2e_f32, d2h_f32 = timed_pipeline("f32")
-    env.observe()
-    env.check()
+    for h in halves:
+        h.check()
+    del halves
 
     # the scalar drop-in (rl_env.py API, one game): what a caller that keeps the reference's loop gets
     scalar = None
@@ -791,7 +809,7 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
                     "what": "EnvPipeline (hanabizero_b200/hanabi_env.py): actions from pinned host memory in, the global "
                             "observation as a bit string (785 bits -> 100 bytes per game, hz_envs_step_observe_bits) + legal "
                             "mask + reward/done/score out to pinned host memory every step, the host picks the next action "
-                            "from the returned mask; two steps in flight on two streams",
+                            "from the returned mask; two half-batches in flight on two streams",
                     "u8": {"value": e2e_u8, "d2h_bytes_per_step": d2h_u8},
                     "f32": {"value": e2e_f32, "d2h_bytes_per_step": d2h_f32}},
             "scalar_dropin_steps_per_s": scalar,

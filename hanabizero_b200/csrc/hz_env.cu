@@ -448,6 +448,11 @@ struct EnvArgs {
   uint8_t* out_global8;
   uint8_t* out_local8;
   uint8_t* out_legal8;
+  // bit-packed result row per game (hz_envs_step_observe_bits): the global observation as ceil(global_dim / 32)
+  // little-endian words (bit j of the observation = word[j >> 5] >> (j & 31) & 1), then legal-move mask, reward,
+  // done, score — everything a host-side caller needs from a step in one ~116-byte row
+  uint32_t* out_bits;
+  int64_t ld_bits;
 };
 
 template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
@@ -471,6 +476,8 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
   MtWindow win = mt_prefetch(mt, mti, lane);
   __syncwarp();
   bool dirty = false;
+  int reward = 0, done = 0, score = 0;
+  bool stepped = false;
   HZ_ESTAMP(0);
 
   if (RESET && (a.reset_mask == nullptr || a.reset_mask[gi])) {  // rl_env.py:249-252
@@ -480,7 +487,8 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
   }
   if (STEP && (a.active == nullptr || a.active[gi])) {  // rl_env.py:413-438
     const int action = a.actions[gi];
-    int reward = 0, done = 0, score = score_of(st, C);
+    stepped = true;
+    score = score_of(st, C);
     if (!move_is_legal(st, g, action)) {  // reference: REQUIRE(MoveIsLegal) aborts the process
       if (lane == 0) atomicCAS(ev.err, 0, gi + 1);
       done = is_terminal(st, g);
@@ -544,21 +552,37 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
     if (og8) store_bits_u8(og8, words, 0, L::GLOBAL, lane);
     if (ol8) store_bits_u8(ol8, words, L::OWN, L::GLOBAL - L::OWN, lane);
     HZ_ESTAMP(7);
-    if (a.out_legal || a.out_legal8) {
+    if (a.out_legal || a.out_legal8 || a.out_bits) {
       // LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all uids at once: lanes first agree on
       // which colours / ranks the partner's hand holds, then each lane tests its own move id
       const int other = (cur + 1) % P, n_me = st[O_HLEN + cur], n_ot = st[O_HLEN + other];
       const int card = lane < n_ot ? st[hand_off(other, lane)] : -1;
       const unsigned cmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card / R) : 0u);
       const unsigned rmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card % R) : 0u);
+      bool ok = false;
       if (lane < g.A) {
-        bool ok;
         if (lane < H) ok = st[O_INFO] < MI && lane < n_me;                      // discard
         else if (lane < 2 * H) ok = lane - H < n_me;                            // play
         else if (lane < 2 * H + C) ok = st[O_INFO] > 0 && ((cmask >> (lane - 2 * H)) & 1u);      // reveal colour
         else ok = st[O_INFO] > 0 && ((rmask >> (lane - 2 * H - C)) & 1u);                        // reveal rank
         if (a.out_legal) a.out_legal[(size_t)gi * g.A + lane] = ok ? 1.0f : 0.0f;
         if (a.out_legal8) a.out_legal8[(size_t)gi * g.A + lane] = ok ? 1 : 0;
+      }
+      if (a.out_bits) {
+        constexpr int GW = (L::GLOBAL + 31) / 32;
+        const unsigned legal_bits = __ballot_sync(HZ_FULL, ok);
+        uint32_t* row = a.out_bits + (size_t)gi * a.ld_bits;
+        if (lane < GW) row[lane] = words[lane];
+        if (!stepped) {   // observe after reset: the episode's running score, nothing finished
+          score = score_of(st, C);
+          done = is_terminal(st, g);
+        }
+        if (lane == 0) {
+          row[GW] = legal_bits;
+          row[GW + 1] = (uint32_t)reward;
+          row[GW + 2] = (uint32_t)done;
+          row[GW + 3] = (uint32_t)score;
+        }
       }
     }
     HZ_ESTAMP(8);
@@ -778,6 +802,65 @@ int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, co
   a.out_global8 = out_global; a.ld_global = ld_global;
   a.out_local8 = out_local; a.ld_local = ld_local; a.out_legal8 = out_legal;
   return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
+}
+
+int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active, int auto_reset,
+                              uint32_t* out_bits, int64_t ld_bits) {
+  if (!e || !out_bits) { set_error("hz_envs_step_observe_bits: NULL argument"); return HZ_ERR_ARG; }
+  if (!e->started) { set_error("hz_envs_step_observe_bits: reset first"); return HZ_ERR_STATE; }
+  const int gw = (e->g.own_len + e->g.enc_len + P + 31) / 32;
+  if (ld_bits < gw + 4) { set_error("hz_envs_step_observe_bits: rows need %d words", gw + 4); return HZ_ERR_ARG; }
+  DeviceGuard dg(e->device);
+  EnvArgs a{};
+  a.actions = actions; a.active = active; a.auto_reset = auto_reset;
+  a.out_bits = out_bits; a.ld_bits = ld_bits;
+  if (actions) return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
+  return launch_env<false, false, true>(e, (cudaStream_t)stream, a);   // actions == NULL: observe only
+}
+
+namespace {
+struct SelTables {
+  uint8_t pop[256];
+  uint8_t sel[256][8];   // sel[v][k] = index of the k-th set bit of v
+  SelTables() {
+    for (int v = 0; v < 256; ++v) {
+      int n = 0;
+      for (int b = 0; b < 8; ++b) {
+        sel[v][b] = 0;
+        if ((v >> b) & 1) sel[v][n++] = (uint8_t)b;
+      }
+      pop[v] = (uint8_t)n;
+    }
+  }
+};
+const SelTables kSel;
+}  // namespace
+
+// Host-side helper for callers that drive the games from the CPU through the packed rows: a uniformly random legal
+// move per game, drawn from the legal-mask word of each row with a counter-based generator (seed, game, step).
+int hz_host_random_legal(const uint32_t* rows, int64_t ld_words, int legal_word, int num_games, int num_actions,
+                         uint64_t seed, uint32_t step, int32_t* out_actions) {
+  if (!rows || !out_actions || num_games < 0 || num_actions <= 0 || num_actions > 32 || legal_word < 0 || ld_words <= legal_word) {
+    set_error("hz_host_random_legal: bad argument");
+    return HZ_ERR_ARG;
+  }
+  const uint32_t amask = num_actions >= 32 ? 0xffffffffu : ((1u << num_actions) - 1u);
+  const unsigned long long step_key = (unsigned long long)step << 32;
+  for (int i = 0; i < num_games; ++i) {
+    uint32_t m = rows[(size_t)i * ld_words + legal_word] & amask;
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)i + 1ull) + step_key;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    // k-th set bit of m without data-dependent branches: per-byte counts, then a 256 x 8 select table
+    const uint32_t b0 = m & 255u, b1 = (m >> 8) & 255u, b2 = (m >> 16) & 255u, b3 = m >> 24;
+    const uint32_t c0 = kSel.pop[b0], c1 = c0 + kSel.pop[b1], c2 = c1 + kSel.pop[b2], c3 = c2 + kSel.pop[b3];
+    const uint32_t k = (uint32_t)(((x >> 32) * c3) >> 32);     // uniform in [0, popcount)
+    const uint32_t byte = (k >= c0) + (k >= c1) + (k >= c2);
+    const uint32_t base = byte == 0 ? 0u : (byte == 1 ? c0 : (byte == 2 ? c1 : c2));
+    const uint32_t bv = (m >> (8 * byte)) & 255u;
+    out_actions[i] = c3 ? (int32_t)(8 * byte + kSel.sel[bv][(k - base) & 7u]) : 0;
+  }
+  return HZ_OK;
 }
 
 #ifdef HZ_TRACE

@@ -131,6 +131,42 @@ class HanabiVecEnv:
                  ptr(self.done), ptr(self.score), ptr(g), self._ld(g), ptr(l), self._ld(l), ptr(a)))
         return g, l, a, self.reward, self.done, self.score
 
+    # -- host-facing form: one bit-packed row per game -------------------------------------------------------------
+    @property
+    def bits_words(self):
+        """Words per packed row: ceil(global_dim / 32) observation words + legal mask + reward + done + score."""
+        return (self.global_dim + 31) // 32 + 4
+
+    def step_bits(self, actions=None, active=None, auto_reset=False, out=None):
+        """One launch: step (actions int32 CUDA [N]; None = observe only) + optional auto-reset + the result of every
+        game as ONE packed uint32 row (include/hzb200.h: hz_envs_step_observe_bits) — int32 CUDA tensor
+        [N, bits_words], written into `out` if given.  ~116 bytes per Hanabi-Full game instead of 3.2 KB of float32."""
+        if out is None:
+            out = torch.empty(self.num_games, self.bits_words, dtype=torch.int32, device=self.device)
+        act = None if active is None else active.to(self.device, torch.uint8).contiguous()
+        check(self._lib.hz_envs_step_observe_bits(self._h, self._stream(), ptr(actions), ptr(act), 1 if auto_reset else 0,
+                                                  ptr(out), out.stride(0)))
+        return out
+
+    def unpack_bits(self, packed):
+        """Packed rows on the HOST (numpy int32/uint32 [n, bits_words] or a CPU tensor) -> dict of numpy arrays:
+        global_obs uint8 [n, global_dim], local_obs uint8 [n, local_dim] (its suffix), legal uint8 [n, A], reward
+        int32 [n], done bool [n], score int32 [n]."""
+        rows = np.ascontiguousarray(packed.numpy() if isinstance(packed, torch.Tensor) else packed).view(np.uint32)
+        w = self.bits_words - 4
+        bits = np.unpackbits(rows[:, :w].view(np.uint8), axis=1, bitorder="little")[:, :self.global_dim]
+        legal = (rows[:, w, None] >> np.arange(self.num_actions, dtype=np.uint32)) & 1
+        return dict(global_obs=bits, local_obs=bits[:, self.own_len:], legal=legal.astype(np.uint8),
+                    reward=rows[:, w + 1].view(np.int32), done=rows[:, w + 2] != 0, score=rows[:, w + 3].view(np.int32))
+
+    def random_legal_host(self, packed_rows, out_actions, seed=0, step=0):
+        """HOST: a uniformly random legal move per game from packed rows in host memory (CPU int32 tensor
+        [n, bits_words]) into `out_actions` (CPU int32 tensor [n], e.g. pinned) — hz_host_random_legal."""
+        check(self._lib.hz_host_random_legal(packed_rows.data_ptr(), packed_rows.stride(0), self.bits_words - 4,
+                                             packed_rows.shape[0], self.num_actions, int(seed) & (2 ** 64 - 1),
+                                             int(step) & 0xffffffff, out_actions.data_ptr()))
+        return out_actions
+
     def check(self):
         """Synchronises and raises IllegalMoveError if any game was handed an illegal move."""
         bad = _lib.C.c_int32(-1)
@@ -141,6 +177,96 @@ class HanabiVecEnv:
         out = torch.empty(self.num_games, self.dump_len, dtype=torch.int32, device=self.device)
         check(self._lib.hz_envs_dump(self._h, self._stream(), ptr(out)))
         return out
+
+
+class EnvPipeline:
+    """Host-driven stepping, double-buffered like mcts.SearchPipeline: the games are held as several independent
+    GROUPS (one HanabiVecEnv each); every group has its own stream on which a step is
+
+        actions from pinned host memory -> one kernel (step + auto-reset + observe) -> result to pinned host memory
+
+    so while the host reads one group's result and chooses its next actions, the other groups' copies and kernels are
+    in flight.  A closed loop over a single batch cannot overlap anything (the next actions depend on the result);
+    two half-batches can.
+
+        pipe = EnvPipeline([env_a, env_b], fmt="bits")
+        for g in range(pipe.groups): pipe.observe_now(g)
+        while True:
+            for g in range(pipe.groups):
+                rows, legal = pipe.wait(g)               # pinned host tensors of group g's last step
+                pipe.step(g, choose(rows, legal))        # pinned int32 [n_g]; returns at once
+
+    fmt: "bits" = packed rows (HanabiVecEnv.step_bits / unpack_bits; `wait` returns (rows int32 [n, W+4], the
+    legal-mask word column [n])); "u8" / "f32" = (global observation [n, D], legal [n, A]) as 0/1 bytes or float32 —
+    what round 1 shipped, kept for comparison (8x / 32x the bytes)."""
+
+    def __init__(self, envs, fmt="bits"):
+        if fmt not in ("bits", "u8", "f32"):
+            raise ValueError("fmt must be 'bits', 'u8' or 'f32'")
+        self.envs = list(envs) if isinstance(envs, (list, tuple)) else [envs]
+        self.fmt, self.groups = fmt, len(self.envs)
+        self.slots = []
+        self.d2h_bytes_per_step = 0
+        for env in self.envs:
+            n, a, dev = env.num_games, env.num_actions, env.device
+            if fmt == "bits":
+                d_obs = torch.zeros(n, env.bits_words, dtype=torch.int32, device=dev)
+                d_leg = d_rds = None
+            else:
+                dt = torch.uint8 if fmt == "u8" else torch.float32
+                pad = (env.global_dim + 15) // 16 * 16 if fmt == "u8" else env.global_dim
+                d_obs = torch.zeros(n, pad, dtype=dt, device=dev)
+                d_leg = torch.zeros(n, a, dtype=dt, device=dev)
+            h_obs = torch.empty(d_obs.shape, dtype=d_obs.dtype).pin_memory()
+            h_leg = None if d_leg is None else torch.empty(d_leg.shape, dtype=d_leg.dtype).pin_memory()
+            self.slots.append(dict(env=env, stream=torch.cuda.Stream(dev), d_act=torch.zeros(n, dtype=torch.int32, device=dev),
+                                   d_obs=d_obs, d_leg=d_leg, h_obs=h_obs, h_leg=h_leg, done=torch.cuda.Event()))
+            self.d2h_bytes_per_step += h_obs.numel() * h_obs.element_size() + (
+                0 if h_leg is None else h_leg.numel() * h_leg.element_size())
+            # everything enqueued on the creating stream so far (reset, ...) precedes the group's own stream
+            self.slots[-1]["stream"].wait_stream(torch.cuda.current_stream(dev))
+
+    def _submit(self, group, h_actions):
+        s = self.slots[group]
+        env = s["env"]
+        with torch.cuda.stream(s["stream"]):
+            acts = None
+            if h_actions is not None:
+                acts = s["d_act"]
+                acts.copy_(h_actions, non_blocking=True)
+            if self.fmt == "bits":
+                env.step_bits(acts, auto_reset=True, out=s["d_obs"])
+            elif acts is None:
+                env.observe(out_global=s["d_obs"][:, :env.global_dim], out_local=None, out_legal=s["d_leg"])
+            else:
+                env.step_all(acts, auto_reset=True, want_local=False, out_global=s["d_obs"][:, :env.global_dim],
+                             out_legal=s["d_leg"])
+            s["h_obs"].copy_(s["d_obs"], non_blocking=True)
+            if s["h_leg"] is not None:
+                s["h_leg"].copy_(s["d_leg"], non_blocking=True)
+            s["done"].record(s["stream"])
+
+    def observe_now(self, group):
+        """Current observation of the group's games (no step)."""
+        self._submit(group, None)
+
+    def step(self, group, h_actions):
+        """Step the group's games with the given actions (pinned host int32 [n]); returns at once."""
+        self._submit(group, h_actions)
+
+    def wait(self, group):
+        """Block until the group's last submission is in host memory; returns (observation rows, legal) host tensors —
+        for fmt="bits": (packed rows [n, W+4] int32, the legal-mask word column [n] int32)."""
+        s = self.slots[group]
+        s["done"].synchronize()
+        if self.fmt == "bits":
+            return s["h_obs"], s["h_obs"][:, s["env"].bits_words - 4]
+        return s["h_obs"], s["h_leg"]
+
+    def drain(self):
+        for s in self.slots:
+            s["done"].synchronize()
+            torch.cuda.current_stream(s["env"].device).wait_stream(s["stream"])
 
 
 class Discrete:
@@ -258,6 +384,10 @@ class HanabiEnv:
         self.observation_space = [[v.enc_len + v.players] for _ in range(v.players)]
         self.share_observation_space = [[v.own_len + v.enc_len + v.players] for _ in range(v.players)]
         self._action = torch.zeros(1, dtype=torch.int32, device=v.device)
+        # one step = action in (4 bytes, pinned) -> one launch -> one packed row out (pinned) -> one synchronise
+        self._h_action = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._d_row = torch.zeros(1, v.bits_words, dtype=torch.int32, device=v.device)
+        self._h_row = torch.zeros(1, v.bits_words, dtype=torch.int32).pin_memory()
 
     def vectorized_observation_shape(self):
         return [self._vec.enc_len]
@@ -268,22 +398,27 @@ class HanabiEnv:
     def num_moves(self):
         return self._vec.num_actions
 
-    def _tuple(self, g, l, a):
-        host = torch.cat((g[0], l[0], a[0])).cpu().numpy()
-        gd, ld = self._vec.global_dim, self._vec.local_dim
-        share_obs = host[:gd].astype(np.int64).tolist()
-        obs = host[gd:gd + ld].astype(np.int64).tolist()
-        legal = list(host[gd + ld:].astype(np.float64))
-        return share_obs, obs, legal
+    def _fetch(self):
+        """Packed row -> host -> the reference's Python lists (rl_env.py:254-263, 426-442)."""
+        self._h_row.copy_(self._d_row, non_blocking=True)
+        torch.cuda.current_stream(self._vec.device).synchronize()
+        u = self._vec.unpack_bits(self._h_row)
+        share_obs = u["global_obs"][0].astype(np.int64).tolist()
+        obs = u["local_obs"][0].astype(np.int64).tolist()
+        legal = list(u["legal"][0].astype(np.float64))
+        return share_obs, obs, legal, int(u["reward"][0]), bool(u["done"][0]), int(u["score"][0])
 
     def reset(self, choose=True):
         """rl_env.py:148-267 -> (share_obs, obs, available_actions)."""
         if not choose:
             # the reference's choose=False branch references undefined names and cannot run
             raise NotImplementedError("reset(choose=False) is broken in the reference (rl_env.py:264-266)")
-        g, l, a = self._vec.reset_all()
+        self._vec.reset_all(observe=False)
+        self._vec.step_bits(None, out=self._d_row)
         self.state = _StateView(self._vec)
-        return self._tuple(g, l, a)
+        share_obs, obs, legal = self._fetch()[:3]
+        self._legal_now = legal      # host copy of the mask: an illegal action is caught before it reaches the device
+        return share_obs, obs, legal
 
     def step(self, action):
         """rl_env.py:292-442 -> (share_obs, obs, reward, done, {'score'}, available_actions)."""
@@ -296,17 +431,23 @@ class HanabiEnv:
             raise ValueError("Expected action as dict or int, got: {}".format(action))  # rl_env.py:415
         if self.state is None:
             raise RuntimeError("step() before reset()")
-        self._action.fill_(uid)
-        g, l, a, reward, done, score = self._vec.step_all(self._action)
-        try:
-            self._vec.check()
-        except _lib.IllegalMoveError as e:
-            if isinstance(action, dict):  # rl_env.py:569-572
-                raise AssertionError("Illegal action: {}".format(action)) from e
-            raise
-        share_obs, obs, legal = self._tuple(g, l, a)
-        rds = torch.stack((reward[0], done[0].int(), score[0])).cpu().tolist()
-        return share_obs, obs, int(rds[0]), bool(rds[1]), {"score": int(rds[2])}, legal
+        if not self._legal_now[uid] if 0 <= uid < len(self._legal_now) else True:
+            # the reference aborts the process here (REQUIRE(MoveIsLegal), hanabi_state.cc:222); the kernel leaves the
+            # game untouched and flags it, which check() turns into the exception
+            self._action.fill_(uid)
+            self._vec.step_all(self._action, observe=False)
+            try:
+                self._vec.check()
+            except _lib.IllegalMoveError as e:
+                if isinstance(action, dict):  # rl_env.py:569-572
+                    raise AssertionError("Illegal action: {}".format(action)) from e
+                raise
+        self._h_action[0] = uid
+        self._action.copy_(self._h_action, non_blocking=True)
+        self._vec.step_bits(self._action, out=self._d_row)
+        share_obs, obs, legal, reward, done, score = self._fetch()
+        self._legal_now = legal
+        return share_obs, obs, reward, done, {"score": score}, legal
 
     def close(self):
         pass

@@ -12,21 +12,16 @@ import torch
 from . import _lib, cytree
 from ._lib import check, ptr
 from .mcts import MCTS
-
-
-def dirichlet_noise(num, actions, alpha, device, generator=None):
-    """np.random.dirichlet([alpha] * A) per root (reanalyze_worker.py:343), drawn on the device."""
-    conc = torch.full((num, actions), float(alpha), device=device)
-    gam = torch._standard_gamma(conc, generator=generator) if generator is not None else torch._standard_gamma(conc)
-    return gam / gam.sum(1, keepdim=True)
+from .selfplay import dirichlet_noise
 
 
 @torch.no_grad()
 def reanalyze_policies(config, model, obs, legal_actions, policy_mask, num_unroll_steps, noises=None, mcts=None,
-                       as_tensor=False):
+                       as_tensor=False, noise_seed=0, noise_step=0):
     """obs [B, obs_dim * stack] (float; host or CUDA), legal_actions [B, A] 0/1, policy_mask [B] (0 = position out
     of its trajectory), B = batch * (num_unroll_steps + 1) in trajectory-major order.  `noises` [B, A] replaces
-    the Dirichlet draw (the reference multiplies its draw by the legal mask, :343; so is this one).
+    the Dirichlet draw (the reference multiplies its draw by the legal mask, :343; so is this one); without it the
+    draw is selfplay.dirichlet_noise(seed=noise_seed, step=noise_step), reproducible on the host.
     Returns batch_policies_re: float64 [batch, num_unroll_steps + 1, A] (numpy, or a CUDA tensor with as_tensor).
     """
     lib = _lib.load()
@@ -44,7 +39,7 @@ def reanalyze_policies(config, model, obs, legal_actions, policy_mask, num_unrol
     with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
         _, logits, hidden = model.initial_inference_device(obs)       # :321-336 (value prefix of a root is 0)
     if noises is None:
-        noises = dirichlet_noise(B, A, getattr(config, "root_dirichlet_alpha", 0.3), dev)
+        noises = dirichlet_noise(B, A, getattr(config, "root_dirichlet_alpha", 0.3), dev, noise_seed, noise_step)
     noises = cytree.as_device(noises, torch.float32, dev, (B, A)) * legal                       # :343
     roots = cytree.Roots(B, A, int(config.num_simulations), device=dev)
     roots.prepare(config.root_exploration_fraction, noises, torch.zeros(B, device=dev), logits.float(), legal.int())

@@ -17,6 +17,30 @@ from .hanabi_env import HanabiVecEnv
 from .mcts import MCTS
 
 
+def dirichlet_noise(num, actions, alpha, device, seed=0, step=0, root_offset=0, legal=None):
+    """np.random.dirichlet([alpha] * A) per root (selfplay_worker.py:279, reanalyze_worker.py:343), drawn on the
+    device from counter-based streams keyed by (seed, step, root_offset + root, action): float32 CUDA [num, actions].
+    `legal` (float [num, actions]) zeroes the entries of illegal actions after normalisation (the reanalyze caller's
+    `noise * legal`).  `dirichlet_noise_host` returns the same numbers, bit for bit, without a GPU."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    out = torch.empty(num, actions, dtype=torch.float32, device=dev)
+    lg = None if legal is None else legal.to(device=dev, dtype=torch.float32).contiguous()
+    check(lib.hz_dirichlet_noise(torch.cuda.current_stream(dev).cuda_stream, ptr(out), num, actions, float(alpha),
+                                 int(seed) & (2 ** 64 - 1), int(step) & 0xffffffff, int(root_offset), ptr(lg)))
+    return out
+
+
+def dirichlet_noise_host(num, actions, alpha, seed=0, step=0, root_offset=0, legal=None):
+    """Host twin of `dirichlet_noise` (hz_host_dirichlet_noise): numpy float32 [num, actions], bit-identical."""
+    lib = _lib.load()
+    out = np.empty((num, actions), np.float32)
+    lg = None if legal is None else np.ascontiguousarray(legal, np.float32)
+    check(lib.hz_host_dirichlet_noise(out.ctypes.data, num, actions, float(alpha), int(seed) & (2 ** 64 - 1),
+                                      int(step) & 0xffffffff, int(root_offset), None if lg is None else lg.ctypes.data))
+    return out
+
+
 def select_action_batch(visit_counts, legal_actions, temperature=1.0, deterministic=True, uniforms=None):
     """Batched select_action on the device.  visit_counts int32 [N, A] CUDA (illegal entries are zeroed
     in place, as the reference mutates its argument), legal_actions float [N, A].  Non-deterministic
@@ -62,9 +86,11 @@ class SelfPlayEngine:
     """N Hanabi games + N trees advanced one move per `step()` entirely on one GPU."""
 
     def __init__(self, num_games, hanabi_name, model, config, seeds=None, mdp="global", stack=4, device=None,
-                 record=False, max_episode_len=128, record_banks=2):
+                 record=False, max_episode_len=128, record_banks=2, noise_seed=0, game_offset=0):
         """record: keep every game's trajectory on the device (hanabizero_b200.trajectory, SURVEY §8f N3);
-        finished episodes are fetched with `self.recorder.flush()`."""
+        finished episodes are fetched with `self.recorder.flush()`.  noise_seed / game_offset key the root
+        exploration noise (dirichlet_noise: move m of game i draws stream (noise_seed, m, game_offset + i)), so the
+        noise of any move can be regenerated on the host with dirichlet_noise_host."""
         self.env = HanabiVecEnv(num_games, hanabi_name, seeds, device=device)
         self.dev, self.n, self.stack, self.mdp = self.env.device, num_games, int(stack), mdp
         self.model, self.config, self.mcts = model, config, MCTS(config)
@@ -74,14 +100,13 @@ class SelfPlayEngine:
         self.lib = _lib.load()
         self._obs = torch.zeros(num_games, self.obs_dim, device=self.dev)
         self._all_done = torch.ones(num_games, dtype=torch.uint8, device=self.dev)
-        alpha = float(getattr(config, "root_dirichlet_alpha", 0.3))
+        self.alpha = float(getattr(config, "root_dirichlet_alpha", 0.3))
+        self.noise_seed, self.game_offset, self.moves = int(noise_seed), int(game_offset), 0
         self.recorder = None
         if record:
             from .trajectory import TrajectoryRecorder
             self.recorder = TrajectoryRecorder(num_games, self.obs_dim, self.env.num_actions, self.stack,
                                                max_episode_len, device=self.dev, banks=record_banks)
-        self._gamma = torch.distributions.Gamma(torch.full((num_games, self.env.num_actions), alpha, device=self.dev),
-                                                torch.ones((), device=self.dev))
 
     def _observe_into(self):
         g, l = (self._obs, None) if self.mdp == "global" else (None, self._obs)
@@ -118,12 +143,12 @@ class SelfPlayEngine:
         zeros = torch.zeros(n, device=self.dev)
         legal_i = self.legal.int()
         if noise:   # np.random.dirichlet([alpha] * A) per root (selfplay_worker.py:279), drawn on the device
-            gam = self._gamma.sample()
-            nz = gam / gam.sum(1, keepdim=True)
+            nz = dirichlet_noise(n, self.env.num_actions, self.alpha, self.dev, self.noise_seed, self.moves, self.game_offset)
             roots.prepare(cfg.root_exploration_fraction, nz, zeros, logits.float(), legal_i)
         else:
             roots.prepare_no_noise(zeros, logits.float(), legal_i)
         self.mcts.run_multi(roots, self.model, hidden)
+        self.moves += 1
         visits, values = roots.get_stats_tensors()
         actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
         # env.step for every game; finished games are re-dealt in the same launch and the observation of the

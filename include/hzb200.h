@@ -213,6 +213,21 @@ int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, co
                             uint8_t* out_global, int64_t ld_global, uint8_t* out_local, int64_t ld_local,
                             uint8_t* out_legal);
 
+/* The host-facing form of the same launch: ONE bit-packed row of uint32 words per game (dev, row stride ld_words >=
+ * W + 4 with W = ceil(global_dim / 32): 25 for Hanabi-Full, 7 for Hanabi-Small):
+ *   words [0, W)   the global observation, bit j = (row[j >> 5] >> (j & 31)) & 1 — the encoder emits 0/1 values
+ *                  (canonical_encoders.cc:441-486), so 785 of them are 100 bytes, not 785 or 3140; the local
+ *                  observation is bits [own_len, global_dim) of the same string (rl_env.py:261-262)
+ *   word  W        legal-move mask, bit a = move uid a is legal (rl_env.py:263)
+ *   words W+1..3   reward (int32), done (0/1), score of the step (rl_env.py:436-442)
+ * actions == NULL observes without stepping (reward 0).  A host caller copies N * (W + 4) * 4 bytes per step. */
+int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active, int auto_reset,
+                              uint32_t* out_bits, int64_t ld_words);
+/* HOST helper for callers that drive the games from the CPU through the packed rows (no device work): a uniformly
+ * random legal move per game from word `legal_word` (= W) of each host row, counter-based (seed, game, step). */
+int hz_host_random_legal(const uint32_t* rows, int64_t ld_words, int legal_word, int num_games, int num_actions,
+                         uint64_t seed, uint32_t step, int32_t* out_actions);
+
 /* sync: returns HZ_ERR_ILLEGAL if any game saw an illegal action since the last check
  * (out_game = first offending game index), clearing the flag. */
 int hz_envs_check(hz_envs* e, void* stream, int32_t* out_game);
@@ -234,6 +249,18 @@ int hz_support_decode(void* stream, const void* logits, int elem_bytes, const fl
 /* ------------------------------------------------------------------------------------------
  * "Next" rows: the hops between a search and the next env step.
  * ------------------------------------------------------------------------------------------ */
+/* Root exploration noise (np.random.dirichlet([alpha] * A) per root, /root/reference/core/selfplay_worker.py:279,
+ * reanalyze_worker.py:343-344) from counter-based streams: Philox4x32-10 keyed by `seed`, counter (block, action,
+ * root_offset + root, step); Gamma(alpha) by Marsaglia-Tsang, normalised in ascending order, rounded to float32.
+ * out float[N][A] (dev).  legal_mask (optional, float[N][A]): entries with mask 0 are zeroed AFTER normalisation, as
+ * the reanalyze caller does.  hz_host_dirichlet_noise is the host twin (host pointers, no device work): the same
+ * arithmetic built from IEEE float64 operations only, bit-identical output — a search can be replayed on the CPU
+ * (e.g. through the reference's own cytree) with exactly the noise the device drew. */
+int hz_dirichlet_noise(void* stream, float* out, int num_roots, int num_actions, double alpha, uint64_t seed,
+                       uint32_t step, uint32_t root_offset, const float* legal_mask);
+int hz_host_dirichlet_noise(float* out, int num_roots, int num_actions, double alpha, uint64_t seed, uint32_t step,
+                            uint32_t root_offset, const float* legal_mask);
+
 /* select_action (/root/reference/core/utils.py:280-295): visits int32[N][A] (dev; counts of illegal
  * actions are zeroed in place like the reference does), legal float[N][A], temperature float[N] or
  * NULL (= 1), uniforms double[N] in [0,1) or NULL (deterministic: first arg-max).  Sampling follows

@@ -198,3 +198,80 @@ def test_byte_observations_equal_float_observations(name, preset):
         f_env.observe(out_global=ug)     # float legal/local with a byte global row
     for e in (f_env, b_env, u_env):
         e.check()
+
+
+@pytest.mark.parametrize("name", ["Hanabi-Full", "Hanabi-Small"])
+def test_bit_packed_rows_equal_float_observations(name):
+    """hz_envs_step_observe_bits: the packed row (observation bits, legal mask, reward, done, score) unpacks to
+    exactly what the float launch returns, for reset, step and auto-reset (finished games re-dealt in the launch)."""
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    N, T = 130, 120
+    seeds = np.arange(N) + 23
+    f_env, p_env = HanabiVecEnv(N, name, seeds), HanabiVecEnv(N, name, seeds)
+    fg, fl, fa = f_env.reset_all()
+    p_env.reset_all(observe=False)
+    rows = p_env.step_bits(None)
+    assert rows.shape == (N, p_env.bits_words) and rows.dtype == torch.int32
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    fr = fd = fs = None
+    resets = 0
+    for t in range(T):
+        u = p_env.unpack_bits(rows.cpu())
+        assert (u["global_obs"] == fg.cpu().numpy()).all(), t
+        assert (u["local_obs"] == fl.cpu().numpy()).all() and (u["legal"] == fa.cpu().numpy()).all(), t
+        if fr is not None:
+            assert (u["reward"] == fr.cpu().numpy()).all() and (u["done"] == fd.cpu().numpy().astype(bool)).all(), t
+            assert (u["score"] == fs.cpu().numpy()).all(), t
+            resets += int(u["done"].sum())
+        else:
+            assert (u["reward"] == 0).all() and not u["done"].any()
+        acts = torch.multinomial(fa, 1, generator=gen).view(-1).int()
+        fg, fl, fa, fr, fd, fs = f_env.step_all(acts, auto_reset=True)
+        rows = p_env.step_bits(acts, auto_reset=True)
+    assert resets > 0
+    assert torch.equal(f_env.dump(), p_env.dump())
+    f_env.check()
+    p_env.check()
+
+
+@pytest.mark.parametrize("fmt", ["bits", "u8", "f32"])
+def test_env_pipeline_matches_direct_stepping(fmt):
+    """EnvPipeline (two groups, each on its own stream: pinned host actions in, kernel, result out) plays exactly the
+    games a plain step loop plays."""
+    from hanabizero_b200.hanabi_env import EnvPipeline, HanabiVecEnv
+    n, T, G = 48, 40, 2
+    seeds = [np.arange(n) + 7 + 1000 * g for g in range(G)]
+    refs = [HanabiVecEnv(n, "Hanabi-Full", sd) for sd in seeds]
+    envs = [HanabiVecEnv(n, "Hanabi-Full", sd) for sd in seeds]
+    A, gd = envs[0].num_actions, envs[0].global_dim
+    ref_g, ref_l = [], []
+    for r, e in zip(refs, envs):
+        g0, _, l0 = r.reset_all()
+        ref_g.append(g0.clone())
+        ref_l.append(l0.clone())
+        e.reset_all(observe=False)
+    pipe = EnvPipeline(envs, fmt=fmt)
+    h_act = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(G)]
+    for g in range(G):
+        pipe.observe_now(g)
+    rng = np.random.default_rng(0)
+    for t in range(T):
+        for g in range(G):
+            obs, leg = pipe.wait(g)
+            if fmt == "bits":
+                u = envs[g].unpack_bits(obs)
+                got_g, got_l = u["global_obs"], u["legal"]
+                assert (((leg.numpy().view(np.uint32)[:, None] >> np.arange(A, dtype=np.uint32)) & 1) == got_l).all()
+            else:
+                got_g, got_l = obs.numpy()[:, :gd], leg.numpy()
+            assert (got_g == ref_g[g].cpu().numpy()).all(), (t, g)
+            assert (got_l == ref_l[g].cpu().numpy()).all(), (t, g)
+            acts = np.array([rng.choice(np.flatnonzero(row)) for row in got_l], np.int32)
+            h_act[g].copy_(torch.from_numpy(acts))
+            pipe.step(g, h_act[g])
+            gg, _, ll, _, _, _ = refs[g].step_all(torch.from_numpy(acts).cuda(), auto_reset=True)
+            ref_g[g], ref_l[g] = gg.clone(), ll.clone()
+    pipe.drain()
+    for r, e in zip(refs, envs):
+        assert torch.equal(r.dump(), e.dump())
+        e.check()
