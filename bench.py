@@ -730,7 +730,7 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
         h.reset_all(observe=False)
     # host policy: a uniformly random legal move per game from the returned legal mask (hz_host_random_legal, a few
     # nanoseconds per game in C; numpy needs ~15 vectorised passes = more than the whole device step)
-    rows_tmp = [torch.zeros(n_g, halves[0].bits_words, dtype=torch.int32) for _ in range(G)]
+    rows_tmp = [torch.zeros(n_g, 4, dtype=torch.int32) for _ in range(G)]
 
     def timed_pipeline(fmt):
         pipe = EnvPipeline(halves, fmt=fmt)
@@ -745,10 +745,10 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
             for gi in range(G):
                 obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
                 if fmt == "bits":
-                    rows = obs
+                    rows = leg                                  # meta rows [n, 4]: word 0 is the legal mask
                 else:                                           # 0/1 rows -> the same mask word
                     rows = rows_tmp[gi]
-                    rows[:, -4] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
+                    rows[:, 0] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
                 halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
                 pipe.step(gi, h_acts[gi])
         pipe.drain()

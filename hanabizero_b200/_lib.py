@@ -58,6 +58,8 @@ SIGNATURES = {
     "hz_host_dirichlet_noise": (_i, [_vp, _i, _i, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
     "hz_select_action": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "hz_stack_push": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i]),
+    "hz_ring_gather": (_i, [_vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _i]),
+    "hz_ring_refill": (_i, [_vp, _vp, _i, _vp, _i, _i, _i]),
     "hz_traj_begin": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "hz_traj_append": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hz_traj_pack": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -71,7 +73,7 @@ SIGNATURES = {
     "hz_envs_step_observe": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "hz_envs_observe_u8": (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "hz_envs_step_observe_u8": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
-    "hz_envs_step_observe_bits": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64]),
+    "hz_envs_step_observe_bits": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "hz_host_random_legal": (_i, [_vp, _i64, _i, _i, _i, C.c_uint64, C.c_uint32, _vp]),
     "hz_envs_check": (_i, [_vp, _vp, _vp]),
     "hz_envs_dump": (_i, [_vp, _vp, _vp]),

@@ -83,8 +83,10 @@ __device__ __forceinline__ void raw_to_floats(const RawRow8<float>& raw, int wid
     if (lane * 8 + k >= width) v[k] = -INFINITY;
 }
 
-// Arithmetic of the decode (core/config.py:210-232): float32 throughout with accurate operations only — libdevice
-// expf (<= 2 ulp), correctly rounded division and square root, no ex2/rsqrt/fast-division shortcuts on the result.
+// Arithmetic of the decode (core/config.py:210-232): float32 throughout.  exp(x - m) is one fused multiply-add into
+// the hardware exp2 unit (MUFU.EX2, 2 ulp — the unit libdevice's own expf ends in; the argument x*log2(e) - m*log2(e)
+// is a single rounding, so a softmax term within e^-20 of the maximum carries <= 1e-6 relative error and the terms
+// that matter <= 3e-7); everything after the sums — the two divisions, the square root — is correctly rounded.
 // The inverse transform
 //     out = sign(v) * (((sqrt(1 + 4 eps (|v| + 1 + eps)) - 1) / (2 eps))^2 - 1) * delta
 // is evaluated in the algebraically identical cancellation-free form: with s = sqrt(1 + 4 eps (|v| + 1 + eps)) and
@@ -124,9 +126,12 @@ __device__ __forceinline__ void decode_partial(const RawRow8<T>& raw, int width,
   raw_to_floats(raw, width, lane, v);
   se = 0.0f;
   sw = 0.0f;
+  const float kLog2e = 1.4426950408889634f;
+  const float nm = __fmul_rn(-m, kLog2e);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const float e = expf(__fsub_rn(v[k], m));
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmaf_rn(v[k], kLog2e, nm)));   // exp(v - m); -inf -> 0
     se = __fadd_rn(se, e);
     sw = __fmaf_rn(e, sp[k], sw);
   }
@@ -193,8 +198,11 @@ __device__ __forceinline__ void warp_decode8_pair(const RawRow8<T>& xa, const Ra
     seb = __fadd_rn(seb, t2);
     swb = __fadd_rn(swb, t3);
   }
-  out_a = decode_finish(sea, swa, delta);
-  out_b = decode_finish(seb, swb, delta);
+  // one pass through the (out-of-line) inverse transform: the lower half-warp finishes row a, the upper half row b
+  const bool lo = lane < 16;
+  const float r = decode_finish(lo ? sea : seb, lo ? swa : swb, delta);
+  out_a = __shfl_sync(HZ_FULL, r, 0);
+  out_b = __shfl_sync(HZ_FULL, r, 16);
 }
 
 template <typename T>

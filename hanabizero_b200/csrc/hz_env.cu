@@ -179,95 +179,108 @@ __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_
   __syncwarp();
 }
 
-__device__ __forceinline__ bool move_is_legal(const uint8_t* st, const Rules& g, int uid) {
-  // hanabi_state.cc:166-219 with the uid map of hanabi_game.cc:159-183
+// LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all move uids at once, as a bit mask (warp-uniform):
+// lanes first agree on which colours / ranks the partner's hand holds, then each lane tests its own move id.
+// No terminal check, like the reference (the mask is non-zero at terminal states).  cur < 0 (chance node): no move.
+__device__ __forceinline__ unsigned legal_mask(const uint8_t* st, const Rules& g, int lane) {
   const int cur = (int8_t)st[O_CUR];
-  if (uid < 0 || uid >= g.A || cur < 0) return false;
-  const int H = g.H;
-  if (uid < H) return st[O_INFO] < g.max_info && uid < st[O_HLEN + cur];
-  uid -= H;
-  if (uid < H) return uid < st[O_HLEN + cur];
-  uid -= H;
-  if (st[O_INFO] == 0) return false;
-  const int t = (cur + 1) % P;  // target_offset is always 1 with two players
-  const int n = st[O_HLEN + t];
-  if (uid < g.C) {
-    for (int k = 0; k < n; ++k)
-      if (st[hand_off(t, k)] / g.R == uid) return true;
-    return false;
+  if (cur < 0) return 0u;
+  const int H = g.H, C = g.C, R = g.R;
+  const int other = (cur + 1) % P, n_me = st[O_HLEN + cur], n_ot = st[O_HLEN + other];
+  const int card = lane < n_ot ? st[hand_off(other, lane)] : -1;
+  const unsigned cmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card / R) : 0u);
+  const unsigned rmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card % R) : 0u);
+  bool ok = false;
+  if (lane < g.A) {
+    if (lane < H) ok = st[O_INFO] < g.max_info && lane < n_me;                       // discard
+    else if (lane < 2 * H) ok = lane - H < n_me;                                     // play
+    else if (lane < 2 * H + C) ok = st[O_INFO] > 0 && ((cmask >> (lane - 2 * H)) & 1u);       // reveal colour
+    else ok = st[O_INFO] > 0 && ((rmask >> (lane - 2 * H - C)) & 1u);                         // reveal rank
   }
-  uid -= g.C;
-  for (int k = 0; k < n; ++k)
-    if (st[hand_off(t, k)] % g.R == uid) return true;
-  return false;
+  return __ballot_sync(HZ_FULL, ok);
 }
 
-__device__ __forceinline__ void remove_from_hand(uint8_t* st, int p, int k) {  // hanabi_hand.cc:87-94
-  const int n = st[O_HLEN + p];
-  for (int j = k; j + 1 < n; ++j)
-    for (int f = 0; f < 5; ++f) st[hand_off(p, j) + f] = st[hand_off(p, j + 1) + f];
-  st[O_HLEN + p] = (uint8_t)(n - 1);
-}
-
-// HanabiState::ApplyMove for a player move (hanabi_state.cc:221-275); lane 0 only
-__device__ __forceinline__ void apply_move(uint8_t* st, const Rules& g, int uid) {
+// HanabiState::ApplyMove for a player move (hanabi_state.cc:221-275), warp-cooperative (all lanes call): the hand
+// shift of RemoveFromHand (hanabi_hand.cc:87-94) moves one byte per lane, RevealColor / RevealRank
+// (hanabi_hand.cc:96-126) update one card per lane, lane 0 keeps the scalar book-keeping.
+__device__ __forceinline__ void apply_move(uint8_t* st, const Rules& g, int uid, int lane) {
   const int H = g.H, R = g.R, me = (int8_t)st[O_CUR];
-  if (st[O_DECK] == 0) st[O_TURNS]--;
-  st[O_LMVALID] = 1;
-  st[O_LMPLAYER] = (uint8_t)me;
-  st[O_LMIDX] = kNone; st[O_LMTGT] = kNone; st[O_LMCOLOR] = kNone; st[O_LMRANK] = kNone;
-  st[O_LMCARD] = kNone; st[O_LMFLAGS] = 0; st[O_LMREVEAL] = 0;
-  if (uid < H) {  // discard
-    st[O_LMTYPE] = MV_DISCARD;
-    st[O_LMIDX] = (uint8_t)uid;
-    if (st[O_INFO] < g.max_info) { st[O_INFO]++; st[O_LMFLAGS] |= 2; }
-    const int c = st[hand_off(me, uid)];
-    st[O_LMCARD] = (uint8_t)c;
-    st[O_DISC + c]++;
-    remove_from_hand(st, me, uid);
-  } else if (uid < 2 * H) {  // play
-    const int k = uid - H;
-    st[O_LMTYPE] = MV_PLAY;
-    st[O_LMIDX] = (uint8_t)k;
-    const int c = st[hand_off(me, k)], col = c / R, rk = c % R;
-    st[O_LMCARD] = (uint8_t)c;
-    if (rk == st[O_FW + col]) {  // AddToFireworks hanabi_state.cc:132-144
-      st[O_FW + col]++;
-      st[O_LMFLAGS] |= 1;
-      if (st[O_FW + col] == R && st[O_INFO] < g.max_info) { st[O_INFO]++; st[O_LMFLAGS] |= 2; }
-    } else {
-      st[O_LIFE]--;
-      st[O_DISC + c]++;
-    }
-    remove_from_hand(st, me, k);
-  } else {
-    const int t = (me + 1) % P;
-    const int n = st[O_HLEN + t];
-    st[O_LMTGT] = 1;
-    st[O_INFO]--;
-    uint8_t reveal = 0;
-    if (uid < 2 * H + g.C) {  // reveal colour (RevealColor hanabi_hand.cc:96-110)
-      const int col = uid - 2 * H;
-      st[O_LMTYPE] = MV_REVEAL_COLOR;
-      st[O_LMCOLOR] = (uint8_t)col;
-      for (int k = 0; k < n; ++k) {
-        const int o = hand_off(t, k);
-        if (st[o] / R == col) { reveal |= 1 << k; st[o + 3] = (uint8_t)col; st[o + 1] = (uint8_t)(1 << col); }
-        else st[o + 1] &= (uint8_t)~(1 << col);
-      }
-    } else {  // reveal rank (RevealRank hanabi_hand.cc:112-126)
-      const int rk = uid - 2 * H - g.C;
-      st[O_LMTYPE] = MV_REVEAL_RANK;
-      st[O_LMRANK] = (uint8_t)rk;
-      for (int k = 0; k < n; ++k) {
-        const int o = hand_off(t, k);
-        if (st[o] % R == rk) { reveal |= 1 << k; st[o + 4] = (uint8_t)rk; st[o + 2] = (uint8_t)(1 << rk); }
-        else st[o + 2] &= (uint8_t)~(1 << rk);
-      }
-    }
-    st[O_LMREVEAL] = reveal;
+  const int t = (me + 1) % P;
+  // ---- read phase: everything any lane needs, before anyone writes
+  const int deck = st[O_DECK], info = st[O_INFO];
+  const bool is_discard = uid < H, is_play = !is_discard && uid < 2 * H;
+  const int k = is_discard ? uid : uid - H;                       // hand slot of a discard / play
+  const int n_me = st[O_HLEN + me], n_t = st[O_HLEN + t];
+  const int c = (is_discard || is_play) ? st[hand_off(me, k)] : 0;
+  // RemoveFromHand: byte j of the mover's hand takes the byte one card further once j is at or past slot k
+  const int hb = O_HAND + me * 5 * 5;
+  uint8_t moved = 0;
+  const bool shift = (is_discard || is_play) && lane < 25 && lane >= 5 * k && lane + 5 < 5 * n_me;
+  if (shift) moved = st[hb + lane + 5];
+  // Reveal*: lane = card slot of the target hand
+  const bool is_color = !is_discard && !is_play && uid < 2 * H + g.C;
+  const int hint = is_color ? uid - 2 * H : uid - 2 * H - g.C;
+  bool match = false;
+  int ko = 0;
+  uint8_t know_mask = 0;
+  if (!is_discard && !is_play && lane < n_t) {
+    ko = hand_off(t, lane);
+    const int card = st[ko];
+    match = (is_color ? card / R : card % R) == hint;
+    know_mask = st[ko + (is_color ? 1 : 2)];
   }
-  advance(st, H);
+  const unsigned reveal = __ballot_sync(HZ_FULL, match);
+  const int fw = is_play ? st[O_FW + c / R] : 0;
+  __syncwarp();
+  // ---- write phase
+  if (shift) st[hb + lane] = moved;
+  if (!is_discard && !is_play && lane < n_t) {
+    if (match) {
+      st[ko + (is_color ? 3 : 4)] = (uint8_t)hint;
+      st[ko + (is_color ? 1 : 2)] = (uint8_t)(1 << hint);
+    } else {
+      st[ko + (is_color ? 1 : 2)] = know_mask & (uint8_t)~(1 << hint);
+    }
+  }
+  if (lane == 0) {
+    if (deck == 0) st[O_TURNS]--;
+    st[O_LMVALID] = 1;
+    st[O_LMPLAYER] = (uint8_t)me;
+    st[O_LMIDX] = kNone; st[O_LMTGT] = kNone; st[O_LMCOLOR] = kNone; st[O_LMRANK] = kNone;
+    st[O_LMCARD] = kNone; st[O_LMREVEAL] = 0;
+    uint8_t flags = 0;
+    if (is_discard) {
+      st[O_LMTYPE] = MV_DISCARD;
+      st[O_LMIDX] = (uint8_t)k;
+      if (info < g.max_info) { st[O_INFO] = (uint8_t)(info + 1); flags |= 2; }
+      st[O_LMCARD] = (uint8_t)c;
+      st[O_DISC + c]++;
+      st[O_HLEN + me] = (uint8_t)(n_me - 1);
+    } else if (is_play) {
+      st[O_LMTYPE] = MV_PLAY;
+      st[O_LMIDX] = (uint8_t)k;
+      st[O_LMCARD] = (uint8_t)c;
+      const int col = c / R, rk = c % R;
+      if (rk == fw) {  // AddToFireworks hanabi_state.cc:132-144
+        st[O_FW + col] = (uint8_t)(fw + 1);
+        flags |= 1;
+        if (fw + 1 == R && info < g.max_info) { st[O_INFO] = (uint8_t)(info + 1); flags |= 2; }
+      } else {
+        st[O_LIFE]--;
+        st[O_DISC + c]++;
+      }
+      st[O_HLEN + me] = (uint8_t)(n_me - 1);
+    } else {
+      st[O_LMTGT] = 1;
+      st[O_INFO] = (uint8_t)(info - 1);
+      st[O_LMTYPE] = is_color ? MV_REVEAL_COLOR : MV_REVEAL_RANK;
+      st[is_color ? O_LMCOLOR : O_LMRANK] = (uint8_t)hint;
+      st[O_LMREVEAL] = (uint8_t)reveal;
+    }
+    st[O_LMFLAGS] = flags;
+  }
+  __syncwarp();
+  if (lane == 0) advance(st, H);
 }
 
 __device__ __forceinline__ int score_of(const uint8_t* st, int C) {  // hanabi_state.cc:359-364
@@ -321,86 +334,108 @@ struct ObsLayout {
   static constexpr int o_info = o_fw + BPC, o_life = o_info + MI, o_disc = o_life + ML, o_last = o_disc + DECK_MAX;
   static constexpr int o_know = o_last + LAST, o_turn = o_know + P * H * PER_CARD, GLOBAL = o_turn + P;
   static constexpr int ENC = GLOBAL - OWN - P, WORDS = (GLOBAL + 31) / 32 + 1;
-  // segment table
-  static constexpr int s_own = 0, s_other = H, s_miss = 2 * H, s_deck = s_miss + 1, s_fw = s_deck + 2;
-  static constexpr int s_info = s_fw + 1, s_life = s_info + 1, s_disc = s_life + 1, s_last = s_disc + C;
-  static constexpr int s_know = s_last + 2, s_turn = s_know + 2 * P * H, SEGS = s_turn + 1;
   static_assert(DW <= 64 && LAST_A <= 32 && BPC + 2 <= 32 && PER_COLOR <= 32, "segment wider than a word");
+  static_assert(2 * H + P * H + C + 1 <= 32, "one lane per segment");
 };
 
+// Every lane prepares at most two (bit offset, value) fields from the game state — the part that differs from lane to
+// lane is plain byte loads and ALU work — and the shared-memory atomics that OR the fields into the bit string are
+// issued afterwards by uniform code, all lanes at once (a per-lane switch around the atomics serialises their ~60-cycle
+// round trips branch after branch):
+//   lanes [0, 2H)         one hand card each (own hand, then the partner's)  + one board field each:
+//                         fireworks, "hand is short" bits, deck (two words), information / life tokens, turn
+//   lanes [2H, 2H + P*H)  card knowledge of one (player, slot): plausible-card grid + hinted colour / rank
+//   next C lanes          discards of one colour
+//   one more lane         the last move (two fields)
 template <int C, int R, int H, int MI, int ML>
-__device__ __forceinline__ void obs_segment(const uint8_t* st, int cur, uint32_t* w, int seg) {
+__device__ __forceinline__ void obs_build(const uint8_t* st, int cur, uint32_t* w, int lane) {
   using L = ObsLayout<C, R, H, MI, ML>;
+  static_assert(2 * H >= 7 || H == 2, "board fields ride on the hand lanes");
   const int other = (cur + 1) % P;
-  if (seg < L::s_other) {  // own hand, slot k
-    const int k = seg;
-    if (k < st[O_HLEN + cur]) or_bits(w, k * L::BPC + st[hand_off(cur, k)], 1u);
-  } else if (seg < L::s_miss) {  // the other player's hand, slot k
-    const int k = seg - L::s_other;
-    if (k < st[O_HLEN + other]) or_bits(w, L::o_hands + k * L::BPC + st[hand_off(other, k)], 1u);
-  } else if (seg == L::s_miss) {  // "hand is short" bits, observer first
-    or_bits(w, L::o_miss, (st[O_HLEN + cur] < H ? 1u : 0u) | (st[O_HLEN + other] < H ? 2u : 0u));
-  } else if (seg < L::s_fw) {  // deck size thermometer (two words)
-    const int n = st[O_DECK];
-    if (seg == L::s_deck) or_bits(w, L::o_deck, ones(n < 32 ? n : 32));
-    else if (n > 32) or_bits(w, L::o_deck + 32, ones(n - 32));
-  } else if (seg == L::s_fw) {  // fireworks: one-hot of (height - 1) per colour
-    uint32_t v = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      if (st[O_FW + c] > 0) v |= 1u << (c * R + st[O_FW + c] - 1);
-    or_bits(w, L::o_fw, v);
-  } else if (seg == L::s_info) {
-    or_bits(w, L::o_info, ones(st[O_INFO]));
-  } else if (seg == L::s_life) {
-    or_bits(w, L::o_life, ones(st[O_LIFE]));
-  } else if (seg < L::s_last) {  // discards of colour c: thermometers of widths 3,2,..,2,1
-    const int c = seg - L::s_disc;
-    uint32_t v = ones(st[O_DISC + c * R]);
-#pragma unroll
-    for (int r = 1; r < R; ++r) v |= ones(st[O_DISC + c * R + r]) << (3 + 2 * (r - 1));
-    or_bits(w, L::o_disc + c * L::PER_COLOR, v);
-  } else if (seg < L::s_know) {  // last non-deal move (observer-relative)
-    if (!st[O_LMVALID]) return;
-    const int ty = st[O_LMTYPE];
-    const bool reveal = ty == MV_REVEAL_COLOR || ty == MV_REVEAL_RANK, pd = ty == MV_PLAY || ty == MV_DISCARD;
-    if (seg == L::s_last) {
-      const int rel = (st[O_LMPLAYER] - cur + P) % P;
-      uint32_t v = 1u << rel;
-      v |= 1u << (P + (ty == MV_PLAY ? 0 : ty == MV_DISCARD ? 1 : ty == MV_REVEAL_COLOR ? 2 : 3));
-      if (reveal) v |= 1u << (P + 4 + (rel + st[O_LMTGT]) % P);
-      if (ty == MV_REVEAL_COLOR) v |= 1u << (P + 4 + P + st[O_LMCOLOR]);
-      if (ty == MV_REVEAL_RANK) v |= 1u << (P + 4 + P + C + st[O_LMRANK]);
-      if (reveal) v |= (uint32_t)(st[O_LMREVEAL] & ((1 << H) - 1)) << (P + 4 + P + C + R);
-      if (pd) v |= 1u << (P + 4 + P + C + R + H + st[O_LMIDX]);
-      or_bits(w, L::o_last, v);
-    } else {
-      uint32_t v = 0;
-      if (pd) v |= 1u << st[O_LMCARD];
-      if (ty == MV_PLAY) v |= (uint32_t)(st[O_LMFLAGS] & 3) << L::BPC;
-      or_bits(w, L::o_last + L::LAST_A, v);
+  int bit0 = 0, bit1 = 0;
+  uint32_t v0 = 0, v1 = 0;
+  if (lane < 2 * H) {
+    // hands (canonical_encoders.cc:66-109, 465-486)
+    const bool own = lane < H;
+    const int k = own ? lane : lane - H, p = own ? cur : other;
+    if (k < st[O_HLEN + p]) {
+      bit0 = (own ? 0 : L::o_hands) + k * L::BPC + st[hand_off(p, k)];
+      v0 = 1u;
     }
-  } else if (seg < L::s_turn) {  // card knowledge: player rel, slot k; part 0 = plausible grid, 1 = hints
-    const int idx = (seg - L::s_know) >> 1, part = (seg - L::s_know) & 1;
-    const int rel = idx / H, k = idx - rel * H, p = (cur + rel) % P;
-    if (k >= st[O_HLEN + p]) return;
-    const int o = hand_off(p, k), base = L::o_know + idx * L::PER_CARD;
-    if (part == 0) {
-      uint32_t v = 0;
-      const uint32_t rm = st[o + 2];
+  } else if (lane < 2 * H + P * H) {
+    // card knowledge (canonical_encoders.cc:370-423): player rel (observer first), slot k
+    const int idx = lane - 2 * H, rel = idx / H, k = idx - rel * H, p = (cur + rel) % P;
+    if (k < st[O_HLEN + p]) {
+      const int o = hand_off(p, k);
+      const uint32_t cm = st[o + 1], rm = st[o + 2];
 #pragma unroll
       for (int c = 0; c < C; ++c)
-        if ((st[o + 1] >> c) & 1) v |= rm << (c * R);
-      or_bits(w, base, v);
-    } else {
-      uint32_t v = 0;
-      if (st[o + 3] != kNone) v |= 1u << st[o + 3];
-      if (st[o + 4] != kNone) v |= 1u << (C + st[o + 4]);
-      or_bits(w, base + L::BPC, v);
+        if ((cm >> c) & 1u) v0 |= rm << (c * R);
+      bit0 = L::o_know + idx * L::PER_CARD;
+      if (st[o + 3] != kNone) v1 |= 1u << st[o + 3];
+      if (st[o + 4] != kNone) v1 |= 1u << (C + st[o + 4]);
+      bit1 = bit0 + L::BPC;
     }
-  } else if (seg == L::s_turn) {
-    or_bits(w, L::o_turn, 1u << cur);
+  } else if (lane < 2 * H + P * H + C) {
+    // discards of one colour: thermometers of widths 3,2,..,2,1 (canonical_encoders.cc:192-215)
+    const int c = lane - 2 * H - P * H;
+    v0 = ones(st[O_DISC + c * R]);
+#pragma unroll
+    for (int r = 1; r < R; ++r) v0 |= ones(st[O_DISC + c * R + r]) << (3 + 2 * (r - 1));
+    bit0 = L::o_disc + c * L::PER_COLOR;
+  } else if (lane == 2 * H + P * H + C) {
+    // last non-deal move, observer-relative (canonical_encoders.cc:240-342)
+    if (st[O_LMVALID]) {
+      const int ty = st[O_LMTYPE];
+      const bool reveal = ty == MV_REVEAL_COLOR || ty == MV_REVEAL_RANK, pd = ty == MV_PLAY || ty == MV_DISCARD;
+      const int rel = (st[O_LMPLAYER] - cur + P) % P;
+      v0 = 1u << rel;
+      v0 |= 1u << (P + (ty == MV_PLAY ? 0 : ty == MV_DISCARD ? 1 : ty == MV_REVEAL_COLOR ? 2 : 3));
+      if (reveal) v0 |= 1u << (P + 4 + (rel + st[O_LMTGT]) % P);
+      if (ty == MV_REVEAL_COLOR) v0 |= 1u << (P + 4 + P + st[O_LMCOLOR]);
+      if (ty == MV_REVEAL_RANK) v0 |= 1u << (P + 4 + P + C + st[O_LMRANK]);
+      if (reveal) v0 |= (uint32_t)(st[O_LMREVEAL] & ((1 << H) - 1)) << (P + 4 + P + C + R);
+      if (pd) v0 |= 1u << (P + 4 + P + C + R + H + st[O_LMIDX]);
+      bit0 = L::o_last;
+      if (pd) v1 |= 1u << st[O_LMCARD];
+      if (ty == MV_PLAY) v1 |= (uint32_t)(st[O_LMFLAGS] & 3) << L::BPC;
+      bit1 = L::o_last + L::LAST_A;
+    }
   }
+  // board fields: second field of the hand lanes (H = 2 leaves four hand lanes: they take two rounds)
+  for (int f = lane; f < 7 && lane < 2 * H; f += 2 * H) {
+    uint32_t v = 0;
+    int bit = 0;
+    const int n = st[O_DECK];
+    if (f == 0) {          // fireworks: one-hot of (height - 1) per colour (canonical_encoders.cc:143-151)
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (st[O_FW + c] > 0) v |= 1u << (c * R + st[O_FW + c] - 1);
+      bit = L::o_fw;
+    } else if (f == 1) {   // "hand is short" bits, observer first
+      v = (st[O_HLEN + cur] < H ? 1u : 0u) | (st[O_HLEN + other] < H ? 2u : 0u);
+      bit = L::o_miss;
+    } else if (f == 2) {   // deck thermometer, first word
+      v = ones(n < 32 ? n : 32);
+      bit = L::o_deck;
+    } else if (f == 3) {   // deck thermometer, second word
+      v = n > 32 ? ones(n - 32) : 0u;
+      bit = L::o_deck + 32;
+    } else if (f == 4) {
+      v = ones(st[O_INFO]);
+      bit = L::o_info;
+    } else if (f == 5) {
+      v = ones(st[O_LIFE]);
+      bit = L::o_life;
+    } else {               // absolute current-player one-hot (rl_env.py:256-257)
+      v = 1u << cur;
+      bit = L::o_turn;
+    }
+    if (f < 2 * H) { v1 = v; bit1 = bit; }
+    else or_bits(w, bit, v);          // only for H = 2 (second round of the four hand lanes)
+  }
+  or_bits(w, bit0, v0);
+  or_bits(w, bit1, v1);
 }
 
 // bits [bit0, bit0 + n) of `words` (one spare word follows the last) as n bytes of 0/1; four bytes per lane
@@ -453,6 +488,7 @@ struct EnvArgs {
   // done, score — everything a host-side caller needs from a step in one ~116-byte row
   uint32_t* out_bits;
   int64_t ld_bits;
+  uint32_t* out_meta;   // optional [N][4]: {legal mask, reward, done, score} kept apart from the observation words
 };
 
 template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
@@ -489,13 +525,14 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
     const int action = a.actions[gi];
     stepped = true;
     score = score_of(st, C);
-    if (!move_is_legal(st, g, action)) {  // reference: REQUIRE(MoveIsLegal) aborts the process
+    const unsigned lm = legal_mask(st, g, lane);
+    if (action < 0 || action >= g.A || !((lm >> action) & 1u)) {  // reference: REQUIRE(MoveIsLegal) aborts the process
       if (lane == 0) atomicCAS(ev.err, 0, gi + 1);
       done = is_terminal(st, g);
     } else {
       const int last_score = score;
       HZ_ESTAMP(1);
-      if (lane == 0) apply_move(st, g, action);
+      apply_move(st, g, action, lane);
       __syncwarp();
       HZ_ESTAMP(2);
       while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
@@ -531,7 +568,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
     uint32_t* words = s_obs[warp];
     for (int i = lane; i < L::WORDS; i += HZ_WARP) words[i] = 0u;
     __syncwarp();
-    for (int seg = lane; seg < L::SEGS; seg += HZ_WARP) obs_segment<C, R, H, MI, ML>(st, cur, words, seg);
+    obs_build<C, R, H, MI, ML>(st, cur, words, lane);
     __syncwarp();
     HZ_ESTAMP(6);
     float* og = a.out_global ? a.out_global + (size_t)gi * a.ld_global : nullptr;
@@ -553,24 +590,14 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
     if (ol8) store_bits_u8(ol8, words, L::OWN, L::GLOBAL - L::OWN, lane);
     HZ_ESTAMP(7);
     if (a.out_legal || a.out_legal8 || a.out_bits) {
-      // LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all uids at once: lanes first agree on
-      // which colours / ranks the partner's hand holds, then each lane tests its own move id
-      const int other = (cur + 1) % P, n_me = st[O_HLEN + cur], n_ot = st[O_HLEN + other];
-      const int card = lane < n_ot ? st[hand_off(other, lane)] : -1;
-      const unsigned cmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card / R) : 0u);
-      const unsigned rmask = __reduce_or_sync(HZ_FULL, card >= 0 ? 1u << (card % R) : 0u);
-      bool ok = false;
+      const unsigned legal_bits = legal_mask(st, g, lane);
       if (lane < g.A) {
-        if (lane < H) ok = st[O_INFO] < MI && lane < n_me;                      // discard
-        else if (lane < 2 * H) ok = lane - H < n_me;                            // play
-        else if (lane < 2 * H + C) ok = st[O_INFO] > 0 && ((cmask >> (lane - 2 * H)) & 1u);      // reveal colour
-        else ok = st[O_INFO] > 0 && ((rmask >> (lane - 2 * H - C)) & 1u);                        // reveal rank
+        const bool ok = (legal_bits >> lane) & 1u;
         if (a.out_legal) a.out_legal[(size_t)gi * g.A + lane] = ok ? 1.0f : 0.0f;
         if (a.out_legal8) a.out_legal8[(size_t)gi * g.A + lane] = ok ? 1 : 0;
       }
       if (a.out_bits) {
         constexpr int GW = (L::GLOBAL + 31) / 32;
-        const unsigned legal_bits = __ballot_sync(HZ_FULL, ok);
         uint32_t* row = a.out_bits + (size_t)gi * a.ld_bits;
         if (lane < GW) row[lane] = words[lane];
         if (!stepped) {   // observe after reset: the episode's running score, nothing finished
@@ -578,10 +605,14 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
           done = is_terminal(st, g);
         }
         if (lane == 0) {
-          row[GW] = legal_bits;
-          row[GW + 1] = (uint32_t)reward;
-          row[GW + 2] = (uint32_t)done;
-          row[GW + 3] = (uint32_t)score;
+          if (a.out_meta) {
+            reinterpret_cast<uint4*>(a.out_meta)[gi] = make_uint4(legal_bits, (uint32_t)reward, (uint32_t)done, (uint32_t)score);
+          } else {
+            row[GW] = legal_bits;
+            row[GW + 1] = (uint32_t)reward;
+            row[GW + 2] = (uint32_t)done;
+            row[GW + 3] = (uint32_t)score;
+          }
         }
       }
     }
@@ -805,15 +836,17 @@ int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, co
 }
 
 int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active, int auto_reset,
-                              uint32_t* out_bits, int64_t ld_bits) {
+                              uint32_t* out_bits, int64_t ld_bits, uint32_t* out_meta) {
   if (!e || !out_bits) { set_error("hz_envs_step_observe_bits: NULL argument"); return HZ_ERR_ARG; }
   if (!e->started) { set_error("hz_envs_step_observe_bits: reset first"); return HZ_ERR_STATE; }
   const int gw = (e->g.own_len + e->g.enc_len + P + 31) / 32;
-  if (ld_bits < gw + 4) { set_error("hz_envs_step_observe_bits: rows need %d words", gw + 4); return HZ_ERR_ARG; }
+  const int need = gw + (out_meta ? 0 : 4);
+  if (ld_bits < need) { set_error("hz_envs_step_observe_bits: rows need %d words", need); return HZ_ERR_ARG; }
+  if (out_meta && ((uintptr_t)out_meta & 15)) { set_error("hz_envs_step_observe_bits: out_meta must be 16-byte aligned"); return HZ_ERR_ARG; }
   DeviceGuard dg(e->device);
   EnvArgs a{};
   a.actions = actions; a.active = active; a.auto_reset = auto_reset;
-  a.out_bits = out_bits; a.ld_bits = ld_bits;
+  a.out_bits = out_bits; a.ld_bits = ld_bits; a.out_meta = out_meta;
   if (actions) return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
   return launch_env<false, false, true>(e, (cudaStream_t)stream, a);   // actions == NULL: observe only
 }

@@ -85,11 +85,11 @@ class HanabiVecEnv:
         if observe:
             return self.observe()
 
-    def observe(self, out_global=None, out_local=None, out_legal=None):
+    def observe(self, out_global=None, out_local=None, out_legal=None, want_local=True, want_global=True):
         """Current player's observation tuple of every game, written into the given (possibly
-        strided: row stride >= dim) float32 CUDA tensors or the env's own buffers."""
-        g = self.global_obs if out_global is None else out_global
-        l = self.local_obs if out_local is None else out_local
+        strided: row stride >= dim) float32 / uint8 CUDA tensors or the env's own buffers."""
+        g = (self.global_obs if out_global is None else out_global) if want_global else None
+        l = (self.local_obs if out_local is None else out_local) if want_local else None
         a = self.legal if out_legal is None else out_legal
         fn = self._lib.hz_envs_observe_u8 if self._all_u8(g, l, a) else self._lib.hz_envs_observe
         check(fn(self._h, self._stream(), ptr(g), self._ld(g), ptr(l), self._ld(l), ptr(a)))
@@ -137,34 +137,41 @@ class HanabiVecEnv:
         """Words per packed row: ceil(global_dim / 32) observation words + legal mask + reward + done + score."""
         return (self.global_dim + 31) // 32 + 4
 
-    def step_bits(self, actions=None, active=None, auto_reset=False, out=None):
+    def step_bits(self, actions=None, active=None, auto_reset=False, out=None, out_meta=None):
         """One launch: step (actions int32 CUDA [N]; None = observe only) + optional auto-reset + the result of every
         game as ONE packed uint32 row (include/hzb200.h: hz_envs_step_observe_bits) — int32 CUDA tensor
-        [N, bits_words], written into `out` if given.  ~116 bytes per Hanabi-Full game instead of 3.2 KB of float32."""
+        [N, bits_words], written into `out` if given.  ~116 bytes per Hanabi-Full game instead of 3.2 KB of float32.
+        With `out_meta` (int32 CUDA [N, 4]) the four trailing words {legal mask, reward, done, score} go there and
+        `out` may be [N, bits_words - 4]."""
         if out is None:
-            out = torch.empty(self.num_games, self.bits_words, dtype=torch.int32, device=self.device)
+            out = torch.empty(self.num_games, self.bits_words - (0 if out_meta is None else 4), dtype=torch.int32,
+                              device=self.device)
         act = None if active is None else active.to(self.device, torch.uint8).contiguous()
         check(self._lib.hz_envs_step_observe_bits(self._h, self._stream(), ptr(actions), ptr(act), 1 if auto_reset else 0,
-                                                  ptr(out), out.stride(0)))
+                                                  ptr(out), out.stride(0), ptr(out_meta)))
         return out
 
-    def unpack_bits(self, packed):
-        """Packed rows on the HOST (numpy int32/uint32 [n, bits_words] or a CPU tensor) -> dict of numpy arrays:
-        global_obs uint8 [n, global_dim], local_obs uint8 [n, local_dim] (its suffix), legal uint8 [n, A], reward
-        int32 [n], done bool [n], score int32 [n]."""
-        rows = np.ascontiguousarray(packed.numpy() if isinstance(packed, torch.Tensor) else packed).view(np.uint32)
+    def unpack_bits(self, packed, meta=None):
+        """Packed rows on the HOST (numpy int32/uint32 [n, bits_words] or a CPU tensor; or observation words [n, W] plus
+        `meta` [n, 4]) -> dict of numpy arrays: global_obs uint8 [n, global_dim], local_obs uint8 [n, local_dim] (its
+        suffix), legal uint8 [n, A], reward int32 [n], done bool [n], score int32 [n]."""
+        as_u32 = lambda x: np.ascontiguousarray(x.numpy() if isinstance(x, torch.Tensor) else x).view(np.uint32)
+        rows = as_u32(packed)
         w = self.bits_words - 4
-        bits = np.unpackbits(rows[:, :w].view(np.uint8), axis=1, bitorder="little")[:, :self.global_dim]
-        legal = (rows[:, w, None] >> np.arange(self.num_actions, dtype=np.uint32)) & 1
+        m = rows[:, w:w + 4] if meta is None else as_u32(meta)
+        bits = np.unpackbits(np.ascontiguousarray(rows[:, :w]).view(np.uint8), axis=1, bitorder="little")[:, :self.global_dim]
+        legal = (m[:, 0, None] >> np.arange(self.num_actions, dtype=np.uint32)) & 1
         return dict(global_obs=bits, local_obs=bits[:, self.own_len:], legal=legal.astype(np.uint8),
-                    reward=rows[:, w + 1].view(np.int32), done=rows[:, w + 2] != 0, score=rows[:, w + 3].view(np.int32))
+                    reward=np.ascontiguousarray(m[:, 1]).view(np.int32), done=m[:, 2] != 0,
+                    score=np.ascontiguousarray(m[:, 3]).view(np.int32))
 
-    def random_legal_host(self, packed_rows, out_actions, seed=0, step=0):
-        """HOST: a uniformly random legal move per game from packed rows in host memory (CPU int32 tensor
-        [n, bits_words]) into `out_actions` (CPU int32 tensor [n], e.g. pinned) — hz_host_random_legal."""
-        check(self._lib.hz_host_random_legal(packed_rows.data_ptr(), packed_rows.stride(0), self.bits_words - 4,
-                                             packed_rows.shape[0], self.num_actions, int(seed) & (2 ** 64 - 1),
-                                             int(step) & 0xffffffff, out_actions.data_ptr()))
+    def random_legal_host(self, rows, out_actions, seed=0, step=0):
+        """HOST: a uniformly random legal move per game into `out_actions` (CPU int32 tensor [n], e.g. pinned) from
+        host rows holding the legal-mask word: packed rows [n, bits_words] (word W) or meta rows [n, 4] (word 0) —
+        hz_host_random_legal."""
+        word = 0 if rows.shape[1] == 4 else self.bits_words - 4
+        check(self._lib.hz_host_random_legal(rows.data_ptr(), rows.stride(0), word, rows.shape[0], self.num_actions,
+                                             int(seed) & (2 ** 64 - 1), int(step) & 0xffffffff, out_actions.data_ptr()))
         return out_actions
 
     def check(self):
@@ -196,9 +203,9 @@ class EnvPipeline:
                 rows, legal = pipe.wait(g)               # pinned host tensors of group g's last step
                 pipe.step(g, choose(rows, legal))        # pinned int32 [n_g]; returns at once
 
-    fmt: "bits" = packed rows (HanabiVecEnv.step_bits / unpack_bits; `wait` returns (rows int32 [n, W+4], the
-    legal-mask word column [n])); "u8" / "f32" = (global observation [n, D], legal [n, A]) as 0/1 bytes or float32 —
-    what round 1 shipped, kept for comparison (8x / 32x the bytes)."""
+    fmt: "bits" = packed (HanabiVecEnv.step_bits / unpack_bits; `wait` returns (observation words int32 [n, W],
+    meta int32 [n, 4] = {legal mask, reward, done, score})); "u8" / "f32" = (global observation [n, D], legal [n, A])
+    as 0/1 bytes or float32 — what round 1 shipped, kept for comparison (8x / 32x the bytes)."""
 
     def __init__(self, envs, fmt="bits"):
         if fmt not in ("bits", "u8", "f32"):
@@ -209,9 +216,9 @@ class EnvPipeline:
         self.d2h_bytes_per_step = 0
         for env in self.envs:
             n, a, dev = env.num_games, env.num_actions, env.device
-            if fmt == "bits":
-                d_obs = torch.zeros(n, env.bits_words, dtype=torch.int32, device=dev)
-                d_leg = d_rds = None
+            if fmt == "bits":      # observation words and the four meta words {legal mask, reward, done, score} apart
+                d_obs = torch.zeros(n, env.bits_words - 4, dtype=torch.int32, device=dev)
+                d_leg = torch.zeros(n, 4, dtype=torch.int32, device=dev)
             else:
                 dt = torch.uint8 if fmt == "u8" else torch.float32
                 pad = (env.global_dim + 15) // 16 * 16 if fmt == "u8" else env.global_dim
@@ -235,9 +242,9 @@ class EnvPipeline:
                 acts = s["d_act"]
                 acts.copy_(h_actions, non_blocking=True)
             if self.fmt == "bits":
-                env.step_bits(acts, auto_reset=True, out=s["d_obs"])
+                env.step_bits(acts, auto_reset=True, out=s["d_obs"], out_meta=s["d_leg"])
             elif acts is None:
-                env.observe(out_global=s["d_obs"][:, :env.global_dim], out_local=None, out_legal=s["d_leg"])
+                env.observe(out_global=s["d_obs"][:, :env.global_dim], out_legal=s["d_leg"], want_local=False)
             else:
                 env.step_all(acts, auto_reset=True, want_local=False, out_global=s["d_obs"][:, :env.global_dim],
                              out_legal=s["d_leg"])
@@ -256,11 +263,9 @@ class EnvPipeline:
 
     def wait(self, group):
         """Block until the group's last submission is in host memory; returns (observation rows, legal) host tensors —
-        for fmt="bits": (packed rows [n, W+4] int32, the legal-mask word column [n] int32)."""
+        for fmt="bits": (observation words [n, W] int32, meta [n, 4] int32 = {legal mask, reward, done, score})."""
         s = self.slots[group]
         s["done"].synchronize()
-        if self.fmt == "bits":
-            return s["h_obs"], s["h_obs"][:, s["env"].bits_words - 4]
         return s["h_obs"], s["h_leg"]
 
     def drain(self):

@@ -178,6 +178,15 @@ class HanabiMuZeroNet(nn.Module):
             plans[dtype] = RecurrentPlan(self, dtype)
         return plans[dtype]
 
+    def initial_plan(self, dtype, frame_dim, stack):
+        """Folded execution plan of initial_inference for eval mode (hanabizero_b200/plan.py InitialPlan), cached."""
+        from .plan import InitialPlan
+        plans = self.__dict__.setdefault("_iplans", {})
+        key = (dtype, int(frame_dim), int(stack))
+        if key not in plans:
+            plans[key] = InitialPlan(self, dtype, frame_dim, stack)
+        return plans[key]
+
     # -- the reference's contract (core/model.py:61-84): numpy on the host in eval mode --------------------
     def initial_inference(self, obs):
         if self.training:

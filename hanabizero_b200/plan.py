@@ -246,3 +246,153 @@ class RecurrentPlan:
         check(self.lib.hz_support_decode(st, ptr(vr), vr.element_size(), ptr(self.support), ptr(dec), 2 * n,
                                          self.n_support, self.P3, self.net.support_delta))
         return dec[:n], dec[n:], ch.policy_logits[:, :self.A].float().contiguous()
+
+
+class InitialPlan:
+    """Execution plan for `initial_inference` in eval mode (representation + policy / value heads;
+    /root/reference/core/model.py:61-72, config/hanabi_control/model.py:127-335) — the per-move counterpart of
+    RecurrentPlan: eval-mode BatchNorm folded, bias / ReLU / residual in the GEMM epilogues, the two heads' first layers
+    one GEMM, their later layers strided batches: 10 (Hanabi-Full) / 5 (Hanabi-Small) cuBLASLt launches instead of the
+    module's ~70 kernels.
+
+    Input layout: the frame stack as [n, stack * frame_stride] with every frame padded to `frame_stride` (a multiple of
+    16) values — what hz_ring_gather writes; the first layer's weight columns are spread out to the same stride (zero
+    columns over the padding), so no repacking of the observation is ever needed."""
+
+    def __init__(self, net, dtype, frame_dim, stack):
+        if dtype not in (torch.float16, torch.float32):
+            raise ValueError("plan dtype must be float16 or float32")
+        self.net, self.dtype = net, dtype
+        self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("InitialPlan needs the module on a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.F, self.A, self.H, self.full = net.feature_size, net.action_space_n, net.hidden_size, net.full
+        self.frame_dim, self.stack = int(frame_dim), int(stack)
+        self.frame_stride = _round_up(self.frame_dim, 16)
+        self.K0 = self.stack * self.frame_stride
+        first = net._representation[0]
+        if first.in_features != self.frame_dim * self.stack:
+            raise ValueError(f"the network takes {first.in_features} inputs, not {self.stack} frames of {self.frame_dim}")
+        self.n_support = net._value_support.numel()
+        self.P3 = _round_up(max(self.n_support, self.A), 16)
+        self.support = net._value_support.detach().float().contiguous()
+        self._sig, self._w, self._bound = None, {}, {}
+        self._modules_cache = None
+        self.refresh(force=True)
+
+    _signature = RecurrentPlan._signature
+    _set = RecurrentPlan._set
+
+    @torch.no_grad()
+    def refresh(self, force=False):
+        sig = self._signature()
+        if not force and sig == self._sig:
+            return False
+        net, rep = self.net, self.net._representation
+        w0, b0 = _fold(rep[0], rep[1])
+        w0p = w0.new_zeros(w0.shape[0], self.K0)       # frame j's columns start at j * frame_stride
+        for j in range(self.stack):
+            w0p[:, j * self.frame_stride:j * self.frame_stride + self.frame_dim] = w0[:, j * self.frame_dim:(j + 1) * self.frame_dim]
+        self._set("W0", w0p)
+        self._set("b0", b0)
+        blocks = [rep[3]] + ([rep[7]] if self.full else [])
+        for i, blk in enumerate(blocks):
+            for nm, (fc, bn) in (("a", (blk.fc1, blk.bn1)), ("b", (blk.fc2, blk.bn2))):
+                w, b = _fold(fc, bn)
+                self._set(f"Wr{i}{nm}", w)
+                self._set(f"br{i}{nm}", b)
+        if self.full:
+            w, b = _fold(rep[4], rep[5])
+            self._set("Wmid", w)
+            self._set("bmid", b)
+        v, p = net._prediction_value, net._prediction_actor
+        order = (p, v) if self.full else (v, p)
+        heads1 = [_fold(h[0], h[1]) for h in order]
+        self._set("Wh1", torch.cat([w for w, _ in heads1]))
+        self._set("bh1", torch.cat([b for _, b in heads1]))
+        if self.full:
+            second = [_fold(p[3].fc1, p[3].bn1), _fold(v[3], v[4])]      # a1 | v2
+            self._set("WB2", torch.stack([w for w, _ in second]))
+            self._set("bB2", torch.stack([b for _, b in second]))
+            wa2, ba2 = _fold(p[3].fc2, p[3].bn2)
+            self._set("Wa2", wa2)
+            self._set("ba2", ba2)
+            fv, fp = v[6], p[4]
+        else:
+            fv, fp = v[3], p[3]
+        outs = [_pad_rows(*_fold(fc, None), self.P3) for fc in (fv, fp)]  # value | policy
+        self._set("WB3", torch.stack([w for w, _ in outs]))
+        self._set("bB3", torch.stack([b for _, b in outs]))
+        self._sig = sig
+        return True
+
+    def bound(self, n):
+        """Static buffers + GEMM chain for batch size n (cached; `x` is the input buffer hz_ring_gather fills)."""
+        b = self._bound.get(n)
+        if b is not None:
+            return b
+        dev, dt, w = self.device, self.dtype, self._w
+        F, H, P3 = self.F, self.H, self.P3
+        z = lambda *shape: torch.zeros(*shape, dtype=dt, device=dev)
+        steps = []
+
+        def step(a, wt, bias, d, m, nn, k, c=None, relu=True, batch=1, sa=0, sw=0, sb=0, sd=0, lda=None, ldc=None):
+            s = GemmStep()
+            s.a, s.lda, s.stride_a = a.data_ptr(), (a.stride(-2) if lda is None else lda), sa
+            s.w, s.ldw, s.stride_w = wt.data_ptr(), wt.stride(-2), sw
+            s.bias, s.stride_bias = bias.data_ptr(), sb
+            s.c, s.ldc, s.stride_c = (0 if c is None else c.data_ptr()), (0 if c is None else (c.stride(-2) if ldc is None else ldc)), 0
+            s.d, s.ldd, s.stride_d = d.data_ptr(), d.stride(-2), sd
+            s.m, s.n, s.k, s.batch, s.relu = m, nn, k, batch, 1 if relu else 0
+            steps.append(s)
+
+        b = type("BoundInitial", (), {})()
+        b.x = z(n, self.K0)
+        b.state = z(n, F)
+        b.h1 = z(n, 2 * H)
+        b.out = z(2, n, P3)
+        if self.full:
+            I = self.net.init_size
+            b.r1, b.t1, b.r2, b.r3, b.t2 = z(n, I), z(n, I), z(n, I), z(n, F), z(n, F)
+            b.xb = z(3, n, H)                                   # [a1, v2, a2]
+            step(b.x, w["W0"], w["b0"], b.r1, n, I, self.K0)
+            step(b.r1, w["Wr0a"], w["br0a"], b.t1, n, I, I)
+            step(b.t1, w["Wr0b"], w["br0b"], b.r2, n, I, I, c=b.r1)
+            step(b.r2, w["Wmid"], w["bmid"], b.r3, n, F, I)
+            step(b.r3, w["Wr1a"], w["br1a"], b.t2, n, F, F)
+            step(b.t2, w["Wr1b"], w["br1b"], b.state, n, F, F, c=b.r3)
+            step(b.state, w["Wh1"], w["bh1"], b.h1, n, 2 * H, F)                     # [actor | value]
+            step(b.h1, w["WB2"], w["bB2"], b.xb, n, H, H, batch=2, sa=H, sw=H * H, sb=H, sd=n * H, lda=2 * H)
+            step(b.xb[0], w["Wa2"], w["ba2"], b.xb[2], n, H, H, c=b.h1)
+            # value logits from v2 (xb[1]), policy logits from a2 (xb[2]): consecutive batches of one strided GEMM
+            step(b.xb[1], w["WB3"], w["bB3"], b.out, n, P3, H, relu=False, batch=2, sa=n * H, sw=P3 * H, sb=P3, sd=n * P3)
+        else:
+            b.r1, b.t1 = z(n, F), z(n, F)
+            step(b.x, w["W0"], w["b0"], b.r1, n, F, self.K0)
+            step(b.r1, w["Wr0a"], w["br0a"], b.t1, n, F, F, c=b.r1)                 # relu(bn1 fc1 x + x)
+            step(b.t1, w["Wr0b"], w["br0b"], b.state, n, F, F)                      # relu(bn2 fc2 .)
+            step(b.state, w["Wh1"], w["bh1"], b.h1, n, 2 * H, F)                     # [value | actor]
+            step(b.h1, w["WB3"], w["bB3"], b.out, n, P3, H, relu=False, batch=2, sa=H, sw=P3 * H, sb=P3, sd=n * P3, lda=2 * H)
+        b.n_steps = len(steps)
+        arr = (GemmStep * b.n_steps)(*steps)
+        b.handle = C.c_void_p()
+        check(self.lib.hz_gemm_plan_create(C.byref(b.handle), dev.index, b.x.element_size(), arr, b.n_steps))
+        if len(self._bound) >= 4:
+            self._bound.pop(next(iter(self._bound)))   # buffers stay alive while a caller holds the object
+        self._bound[n] = b
+        return b
+
+    @torch.no_grad()
+    def run(self, n, decode_value=False):
+        """Runs the chain on bound(n).x (already filled).  Returns (value [n] or None, policy_logits [n, A] float32,
+        hidden_state [n, F] plan dtype) — views of the plan's buffers, valid until the next run."""
+        b = self.bound(n)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        check(self.lib.hz_gemm_plan_run(b.handle, st, 0, b.n_steps))
+        value = None
+        if decode_value:
+            value = torch.empty(n, dtype=torch.float32, device=self.device)
+            check(self.lib.hz_support_decode(st, ptr(b.out[0]), b.out.element_size(), ptr(self.support), ptr(value), n,
+                                             self.n_support, self.P3, self.net.support_delta))
+        return value, b.out[1][:, :self.A].float(), b.state

@@ -100,6 +100,16 @@ class SelfPlayEngine:
         self.lib = _lib.load()
         self._obs = torch.zeros(num_games, self.obs_dim, device=self.dev)
         self._all_done = torch.ones(num_games, dtype=torch.uint8, device=self.dev)
+        # fast path (no recording): the frame stack is a ring of 0/1 bytes the env kernel writes into, and the root
+        # inference runs as a folded GEMM plan (hanabizero_b200/plan.py InitialPlan) instead of ~70 module kernels
+        self.iplan = None
+        if not record and hasattr(model, "initial_plan"):
+            amp = getattr(config, "amp_type", "none") == "torch_amp"
+            self.iplan = model.initial_plan(torch.float16 if amp else torch.float32, self.obs_dim, self.stack)
+            self.Dp = self.iplan.frame_stride
+            self.ring = torch.zeros(num_games, self.stack, self.Dp, dtype=torch.uint8, device=self.dev)
+            self.legal8 = torch.zeros(num_games, self.env.num_actions, dtype=torch.uint8, device=self.dev)
+            self.head = 0          # ring slot holding the OLDEST frame (the next one to be overwritten)
         self.alpha = float(getattr(config, "root_dirichlet_alpha", 0.3))
         self.noise_seed, self.game_offset, self.moves = int(noise_seed), int(game_offset), 0
         self.recorder = None
@@ -123,22 +133,54 @@ class SelfPlayEngine:
         check(self.lib.hz_stack_push(torch.cuda.current_stream(self.dev).cuda_stream, ptr(self.frames), ptr(self._obs),
                                      self._obs.stride(0), ptr(done), self.n, self.stack, self.obs_dim))
 
+    def _ring_slot(self, slot):
+        """(out_global, out_local) views of ring slot `slot` for the env kernel's byte outputs."""
+        row = self.ring[:, slot, :self.obs_dim]
+        return (row, None) if self.mdp == "global" else (None, row)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
     def reset(self):
         """env.reset() for every game; the first observation fills the whole stack (selfplay_worker.py:137)."""
         self.env.reset_all(observe=False)
+        if self.iplan is not None:
+            g, l = self._ring_slot(0)
+            self.env.observe(out_global=g, out_local=l, out_legal=self.legal8, want_global=g is not None,
+                             want_local=l is not None)
+            check(self.lib.hz_ring_refill(self._stream(), ptr(self.ring), 0, None, self.n, self.stack, self.Dp))
+            self.head = 0
+            self.legal.copy_(self.legal8)
+            return self.frames_tensor(), self.legal
         self._observe()
         self._push(self._all_done)
         if self.recorder is not None:
             self.recorder.begin(self._obs, self.legal)
         return self.frames.view(self.n, -1), self.legal
 
+    def frames_tensor(self):
+        """The stacked observation [N, stack * obs_dim] float32, oldest frame first (what the reference feeds
+        initial_inference, core/game.py:169-174)."""
+        if self.iplan is None:
+            return self.frames.view(self.n, -1)
+        order = [(self.head + j) % self.stack for j in range(self.stack)]
+        return self.ring[:, order, :self.obs_dim].float().reshape(self.n, -1)
+
     @torch.no_grad()
     def step(self, temperature=1.0, deterministic=False, noise=True):
         """One self-play move for every game.  Returns a dict of CUDA tensors."""
         cfg, n = self.config, self.n
         amp = getattr(cfg, "amp_type", "none") == "torch_amp"
-        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
-            _, logits, hidden = self.model.initial_inference_device(self.frames.view(n, -1))
+        if self.iplan is not None:
+            self.model.eval()
+            self.iplan.refresh()
+            b = self.iplan.bound(n)
+            check(self.lib.hz_ring_gather(self._stream(), ptr(self.ring), self.head, ptr(b.x), b.x.stride(0), self.Dp, n,
+                                          self.stack, self.Dp, b.x.element_size()))
+            _, logits, hidden = self.iplan.run(n)
+        else:
+            with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+                _, logits, hidden = self.model.initial_inference_device(self.frames.view(n, -1))
         roots = cytree.Roots(n, self.env.num_actions, cfg.num_simulations, device=self.dev)
         zeros = torch.zeros(n, device=self.dev)
         legal_i = self.legal.int()
@@ -153,6 +195,18 @@ class SelfPlayEngine:
         actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
         # env.step for every game; finished games are re-dealt in the same launch and the observation of the
         # current player is written straight into the staging row that feeds the frame stack
+        if self.iplan is not None:
+            # the new observation replaces the oldest frame in place; finished games get their stack refilled
+            slot = self.head
+            g, l = self._ring_slot(slot)
+            _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=True, out_global=g, out_local=l,
+                                                             out_legal=self.legal8, want_global=g is not None,
+                                                             want_local=l is not None)
+            check(self.lib.hz_ring_refill(self._stream(), ptr(self.ring), slot, ptr(done), n, self.stack, self.Dp))
+            self.head = (slot + 1) % self.stack
+            self.legal.copy_(self.legal8)
+            return dict(action=actions, reward=reward.clone(), done=done.clone(), score=score.clone(), visits=visits,
+                        root_value=values, entropy=entropy)
         g, l = self._observe_into()
         if self.recorder is None:
             _, _, _, reward, done, score = self.env.step_all(actions, auto_reset=True, out_global=g, out_local=l,

@@ -220,9 +220,12 @@ int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, co
  *                  observation is bits [own_len, global_dim) of the same string (rl_env.py:261-262)
  *   word  W        legal-move mask, bit a = move uid a is legal (rl_env.py:263)
  *   words W+1..3   reward (int32), done (0/1), score of the step (rl_env.py:436-442)
- * actions == NULL observes without stepping (reward 0).  A host caller copies N * (W + 4) * 4 bytes per step. */
+ * actions == NULL observes without stepping (reward 0).  A host caller copies N * (W + 4) * 4 bytes per step.
+ * out_meta (optional, dev uint32[N][4], 16-byte aligned): the four trailing words {legal mask, reward, done, score} go
+ * there instead (rows then need only W words) — a host policy that looks at the legal mask reads 16 contiguous bytes
+ * per game instead of one word out of every 116-byte row. */
 int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active, int auto_reset,
-                              uint32_t* out_bits, int64_t ld_words);
+                              uint32_t* out_bits, int64_t ld_words, uint32_t* out_meta);
 /* HOST helper for callers that drive the games from the CPU through the packed rows (no device work): a uniformly
  * random legal move per game from word `legal_word` (= W) of each host row, counter-based (seed, game, step). */
 int hz_host_random_legal(const uint32_t* rows, int64_t ld_words, int legal_word, int num_games, int num_actions,
@@ -273,6 +276,18 @@ int hz_select_action(void* stream, int32_t* visits, const float* legal, const fl
  * (first frame of the next episode replicated, selfplay_worker.py:137). */
 int hz_stack_push(void* stream, float* stack, const float* obs, int64_t ld_obs, const uint8_t* done, int num,
                   int stack_depth, int dim);
+
+/* The same frame stack as a RING of 0/1 bytes: ring uint8[N][stack_depth][padded_dim] (dev; padded_dim = frame length
+ * rounded up to 16).  The env kernel writes every new observation straight into the slot holding the oldest frame
+ * (hz_envs_step_observe_u8 with that slot as its output row), so a move costs no memmove at all.
+ * hz_ring_gather: the network input in frame order, oldest first: out[i][j * frame_stride + d] =
+ *   ring[i][(head + j) % stack_depth][d] as half (elem_bytes 2) or float (4); frame_stride >= padded_dim, both
+ *   multiples of 16 (the first layer's weight columns are laid out with the same stride).
+ * hz_ring_refill: games with done[i] != 0 (NULL = all) get slot src_slot copied into every other slot — the first
+ *   observation of a new episode fills the whole stack (core/selfplay_worker.py:137). */
+int hz_ring_gather(void* stream, const uint8_t* ring, int head, void* out, int64_t ld_out, int frame_stride, int num,
+                   int stack_depth, int padded_dim, int elem_bytes);
+int hz_ring_refill(void* stream, uint8_t* ring, int src_slot, const uint8_t* done, int num, int stack_depth, int padded_dim);
 
 /* Trajectory record of N self-play games in HBM: GameHistory.init /
  * store_search_stats / append / game_over (/root/reference/core/game.py:73-93,143-148,176-204) for a

@@ -259,9 +259,12 @@ def test_env_pipeline_matches_direct_stepping(fmt):
         for g in range(G):
             obs, leg = pipe.wait(g)
             if fmt == "bits":
-                u = envs[g].unpack_bits(obs)
+                u = envs[g].unpack_bits(obs, leg)
                 got_g, got_l = u["global_obs"], u["legal"]
-                assert (((leg.numpy().view(np.uint32)[:, None] >> np.arange(A, dtype=np.uint32)) & 1) == got_l).all()
+                assert obs.shape == (n, envs[g].bits_words - 4) and leg.shape == (n, 4)
+                picked = torch.zeros(n, dtype=torch.int32)
+                envs[g].random_legal_host(leg, picked, seed=3, step=t)
+                assert (got_l[np.arange(n), picked.numpy()] == 1).all()      # the host helper only picks legal moves
             else:
                 got_g, got_l = obs.numpy()[:, :gd], leg.numpy()
             assert (got_g == ref_g[g].cpu().numpy()).all(), (t, g)

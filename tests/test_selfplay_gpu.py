@@ -64,11 +64,13 @@ def test_selfplay_engine_steps_on_device(mdp):
     eng = SelfPlayEngine(N, "Hanabi-Full", model, SearchConfig(num_simulations=S), seeds=np.arange(N), mdp=mdp, stack=stack)
     obs, legal = eng.reset()
     assert obs.shape == (N, dim * stack)
-    assert torch.equal(eng.frames[:, 0], eng.frames[:, -1])       # first frame replicated
+    assert eng.iplan is not None                                  # ring of bytes + folded root inference
+    fr = lambda: eng.frames_tensor().view(N, stack, dim)          # frame order: oldest first (core/game.py:169-174)
+    assert torch.equal(fr()[:, 0], fr()[:, -1])                   # first frame replicated
     total_done = 0
     for t in range(8):
         legal_before = eng.legal.clone()
-        prev_last = eng.frames[:, -1].clone()
+        prev_last = fr()[:, -1].clone()
         out = eng.step(temperature=1.0, deterministic=(t % 2 == 0))
         a = out["action"].long()
         assert (legal_before.gather(1, a[:, None]) == 1).all()    # only legal moves are played
@@ -76,11 +78,11 @@ def test_selfplay_engine_steps_on_device(mdp):
         d = out["done"].bool()
         total_done += int(d.sum())
         # frame stack: shifted for running games, refilled for restarted ones
-        assert torch.equal(eng.frames[~d][:, -2], prev_last[~d])
+        assert torch.equal(fr()[~d][:, -2], prev_last[~d])
         if d.any():
-            assert torch.equal(eng.frames[d][:, 0], eng.frames[d][:, -1])
+            assert torch.equal(fr()[d][:, 0], fr()[d][:, -1]) and torch.equal(fr()[d][:, 1], fr()[d][:, 2])
         ref_obs = eng.env.observe()[0 if mdp == "global" else 1]
-        assert torch.equal(eng.frames[:, -1], ref_obs)
+        assert torch.equal(fr()[:, -1], ref_obs)
     eng.env.check()
 
 
@@ -162,7 +164,7 @@ def test_selfplay_engine_noise_is_reproducible_on_the_host():
     eng = SelfPlayEngine(N, "Hanabi-Full", model, cfg, seeds=np.arange(N), noise_seed=77, game_offset=100, device=dev)
     frames, legal = eng.reset()
     eng.step()                                    # move 0
-    frames, legal = eng.frames.view(N, -1).clone(), eng.legal.clone()
+    frames, legal = eng.frames_tensor().clone(), eng.legal.clone()
     out = eng.step(deterministic=True)            # move 1: its noise is stream (77, 1, 100 + i)
     noise = dirichlet_noise_host(N, A, cfg.root_dirichlet_alpha, seed=77, step=1, root_offset=100)
     with torch.no_grad():
@@ -172,3 +174,41 @@ def test_selfplay_engine_noise_is_reproducible_on_the_host():
     MCTS(cfg).run_multi(roots, model, hidden)
     want = roots.get_distributions_tensor() * (legal > 0).int()     # select_action zeroes the counts of illegal moves
     assert torch.equal(want, out["visits"])
+
+
+@pytest.mark.parametrize("small", [False, True])
+def test_initial_plan_matches_the_module(small):
+    """InitialPlan (BN folded, 10 / 5 cuBLASLt GEMMs, frames at a 16-aligned stride) computes initial_inference:
+    float32 plan vs the float32 module within 1e-4, the float16 plan within fp16 rounding."""
+    from hanabizero_b200 import _lib
+    from hanabizero_b200.model import MuZeroNet, MuZeroNetFull
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    D, S, A, n = (193, 4, 11, 77) if small else (785, 4, 20, 300)
+    model = (MuZeroNet if small else MuZeroNetFull)(D * S, A).randomize_heads().to(dev)
+    model.train()
+    with torch.no_grad():                      # non-trivial BatchNorm statistics
+        for _ in range(3):
+            model.initial_inference((torch.rand(64, D * S, device=dev) < 0.2).float())
+    model.eval()
+    frames = (torch.rand(n, S, D, device=dev) < 0.2).to(torch.uint8)
+    lib = _lib.load()
+    with torch.no_grad():
+        value, logits, state = model.initial_inference_device(frames.float().view(n, -1))
+    for dtype, tol in ((torch.float32, 2e-4), (torch.float16, 3e-2)):
+        plan = model.initial_plan(dtype, D, S)
+        Dp = plan.frame_stride
+        ring = torch.zeros(n, S, Dp, dtype=torch.uint8, device=dev)
+        head = 2
+        for j in range(S):                     # logical frame j lives in ring slot (head + j) % S
+            ring[:, (head + j) % S, :D] = frames[:, j]
+        b = plan.bound(n)
+        _lib.check(lib.hz_ring_gather(torch.cuda.current_stream().cuda_stream, ring.data_ptr(), head, b.x.data_ptr(),
+                                      b.x.stride(0), Dp, n, S, Dp, b.x.element_size()))
+        want_x = torch.zeros(n, S, Dp, device=dev)
+        want_x[:, :, :D] = frames.float()
+        assert torch.equal(b.x.float().view(n, S, Dp), want_x)
+        v, lg, st = plan.run(n, decode_value=True)
+        torch.testing.assert_close(st.float(), state.float(), rtol=tol, atol=tol)
+        torch.testing.assert_close(lg, logits, rtol=tol, atol=tol)
+        torch.testing.assert_close(v, value, rtol=10 * tol, atol=10 * tol)
