@@ -733,24 +733,49 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
     rows_tmp = [torch.zeros(n_g, 4, dtype=torch.int32) for _ in range(G)]
 
     def timed_pipeline(fmt):
+        """One host thread per half-batch (the ctypes calls and the graph launches release the GIL): each thread loops
+        wait -> pick -> step on its own group, so one half's host work overlaps the other half's device work."""
         pipe = EnvPipeline(halves, fmt=fmt)
-        h_acts = [torch.zeros(n_g, dtype=torch.int32).pin_memory() for _ in range(G)]
+        h_acts = [pipe.actions(gi) for gi in range(G)]          # the pipeline's own pinned action buffers
         shifts = np.arange(A, dtype=np.uint32)
         for gi in range(G):
             pipe.observe_now(gi)
-        for step in range(5 + T_host):
-            if step == 5:
-                barrier()
-                e0.record()
-            for gi in range(G):
-                obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
-                if fmt == "bits":
-                    rows = leg                                  # meta rows [n, 4]: word 0 is the legal mask
-                else:                                           # 0/1 rows -> the same mask word
-                    rows = rows_tmp[gi]
-                    rows[:, 0] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
-                halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
-                pipe.step(gi, h_acts[gi])
+        warm = threading.Barrier(G + 1)
+        errors = []
+
+        def drive(gi):
+            try:
+                torch.cuda.set_device(dev)
+                for step in range(5 + T_host):
+                    if step == 5:
+                        warm.wait()      # main thread: barrier + start event
+                        warm.wait()
+                    obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
+                    if fmt == "bits":
+                        rows = leg                                  # meta rows [n, 4]: word 0 is the legal mask
+                    else:                                           # 0/1 rows -> the same mask word
+                        rows = rows_tmp[gi]
+                        rows[:, 0] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
+                    halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
+                    pipe.step(gi)
+            except Exception as exc:      # surfaced by the main thread
+                errors.append(exc)
+                try:
+                    warm.abort()
+                except Exception:
+                    pass
+
+        threads = [threading.Thread(target=drive, args=(gi,), daemon=True) for gi in range(G)]
+        for th in threads:
+            th.start()
+        warm.wait()
+        barrier()
+        e0.record()
+        warm.wait()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
         pipe.drain()
         e1.record()
         barrier()
@@ -809,7 +834,8 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
                     "what": "EnvPipeline (hanabizero_b200/hanabi_env.py): actions from pinned host memory in, the global "
                             "observation as a bit string (785 bits -> 100 bytes per game, hz_envs_step_observe_bits) + legal "
                             "mask + reward/done/score out to pinned host memory every step, the host picks the next action "
-                            "from the returned mask; two half-batches in flight on two streams",
+                            "from the returned mask (hz_host_random_legal); two half-batches in flight on two streams, each "
+                            "half-step one CUDA graph launch, one host thread per half",
                     "u8": {"value": e2e_u8, "d2h_bytes_per_step": d2h_u8},
                     "f32": {"value": e2e_f32, "d2h_bytes_per_step": d2h_f32}},
             "scalar_dropin_steps_per_s": scalar,

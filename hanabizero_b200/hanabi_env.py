@@ -207,11 +207,11 @@ class EnvPipeline:
     meta int32 [n, 4] = {legal mask, reward, done, score})); "u8" / "f32" = (global observation [n, D], legal [n, A])
     as 0/1 bytes or float32 — what round 1 shipped, kept for comparison (8x / 32x the bytes)."""
 
-    def __init__(self, envs, fmt="bits"):
+    def __init__(self, envs, fmt="bits", use_graphs=True):
         if fmt not in ("bits", "u8", "f32"):
             raise ValueError("fmt must be 'bits', 'u8' or 'f32'")
         self.envs = list(envs) if isinstance(envs, (list, tuple)) else [envs]
-        self.fmt, self.groups = fmt, len(self.envs)
+        self.fmt, self.groups, self.use_graphs = fmt, len(self.envs), bool(use_graphs)
         self.slots = []
         self.d2h_bytes_per_step = 0
         for env in self.envs:
@@ -227,39 +227,64 @@ class EnvPipeline:
             h_obs = torch.empty(d_obs.shape, dtype=d_obs.dtype).pin_memory()
             h_leg = None if d_leg is None else torch.empty(d_leg.shape, dtype=d_leg.dtype).pin_memory()
             self.slots.append(dict(env=env, stream=torch.cuda.Stream(dev), d_act=torch.zeros(n, dtype=torch.int32, device=dev),
+                                   h_act=torch.zeros(n, dtype=torch.int32).pin_memory(), graph=None, steps=0,
                                    d_obs=d_obs, d_leg=d_leg, h_obs=h_obs, h_leg=h_leg, done=torch.cuda.Event()))
             self.d2h_bytes_per_step += h_obs.numel() * h_obs.element_size() + (
                 0 if h_leg is None else h_leg.numel() * h_leg.element_size())
             # everything enqueued on the creating stream so far (reset, ...) precedes the group's own stream
             self.slots[-1]["stream"].wait_stream(torch.cuda.current_stream(dev))
 
-    def _submit(self, group, h_actions):
-        s = self.slots[group]
+    def actions(self, group):
+        """The group's pinned action buffer (int32 [n]): fill it in place and call step(group) to skip one host copy."""
+        return self.slots[group]["h_act"]
+
+    def _enqueue(self, s, with_actions):
+        """actions in -> kernel -> results out, on the current stream (eager, or under graph capture)."""
         env = s["env"]
-        with torch.cuda.stream(s["stream"]):
-            acts = None
-            if h_actions is not None:
-                acts = s["d_act"]
-                acts.copy_(h_actions, non_blocking=True)
-            if self.fmt == "bits":
-                env.step_bits(acts, auto_reset=True, out=s["d_obs"], out_meta=s["d_leg"])
-            elif acts is None:
-                env.observe(out_global=s["d_obs"][:, :env.global_dim], out_legal=s["d_leg"], want_local=False)
-            else:
-                env.step_all(acts, auto_reset=True, want_local=False, out_global=s["d_obs"][:, :env.global_dim],
-                             out_legal=s["d_leg"])
-            s["h_obs"].copy_(s["d_obs"], non_blocking=True)
-            if s["h_leg"] is not None:
-                s["h_leg"].copy_(s["d_leg"], non_blocking=True)
-            s["done"].record(s["stream"])
+        acts = None
+        if with_actions:
+            acts = s["d_act"]
+            acts.copy_(s["h_act"], non_blocking=True)
+        if self.fmt == "bits":
+            env.step_bits(acts, auto_reset=True, out=s["d_obs"], out_meta=s["d_leg"])
+        elif acts is None:
+            env.observe(out_global=s["d_obs"][:, :env.global_dim], out_legal=s["d_leg"], want_local=False)
+        else:
+            env.step_all(acts, auto_reset=True, want_local=False, out_global=s["d_obs"][:, :env.global_dim],
+                         out_legal=s["d_leg"])
+        s["h_obs"].copy_(s["d_obs"], non_blocking=True)
+        if s["h_leg"] is not None:
+            s["h_leg"].copy_(s["d_leg"], non_blocking=True)
 
     def observe_now(self, group):
         """Current observation of the group's games (no step)."""
-        self._submit(group, None)
+        s = self.slots[group]
+        with torch.cuda.stream(s["stream"]):
+            self._enqueue(s, False)
+            s["done"].record(s["stream"])
 
-    def step(self, group, h_actions):
-        """Step the group's games with the given actions (pinned host int32 [n]); returns at once."""
-        self._submit(group, h_actions)
+    def step(self, group, h_actions=None):
+        """Step the group's games with the given actions (host int32 [n]; None = the buffer from `actions(group)` was
+        filled in place); returns at once.  After two eager steps the group's four operations (actions in, kernel,
+        observation out, meta out) are captured once and replayed as one CUDA graph launch: the host-side cost of a
+        step is what bounds a host-driven loop."""
+        s = self.slots[group]
+        if h_actions is not None and h_actions.data_ptr() != s["h_act"].data_ptr():
+            s["h_act"].copy_(h_actions)
+        with torch.cuda.stream(s["stream"]):
+            if s["graph"] is None and s["steps"] >= 2 and self.use_graphs:
+                s["stream"].synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s["stream"]):
+                    self._enqueue(s, True)
+                s["graph"] = g
+                # the capture only recorded the step: it has not run yet
+            if s["graph"] is not None:
+                s["graph"].replay()
+            else:
+                self._enqueue(s, True)
+            s["done"].record(s["stream"])
+        s["steps"] += 1
 
     def wait(self, group):
         """Block until the group's last submission is in host memory; returns (observation rows, legal) host tensors —
