@@ -70,6 +70,8 @@ def parse_args():
     p.add_argument("--env-steps", type=int, default=200, help="env steps per timed env pass")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--in-flight", type=int, default=4,
+                   help="independent searches kept in flight per GPU (SearchPipeline depth); 1 = one search at a time")
     p.add_argument("--quick", action="store_true", help="search + roofline only (skip env / self-play / extras)")
     return p.parse_args()
 
@@ -416,6 +418,26 @@ class SearchBench:
         self.mcts = MCTS(self.cfg)
         self.holder = [None]
         self.ticket = None
+        self.pipe, self.pipe_ticket = None, None
+
+    def pipelined_step(self):
+        """The same search through SearchPipeline with device-resident inputs: `--in-flight` independent searches on
+        their own streams (and the statistics all_gather of each, off the compute streams)."""
+        if self.pipe is None:
+            from hanabizero_b200.dist import AsyncStatsGather
+            from hanabizero_b200.mcts import SearchPipeline
+            depth = max(1, self.args.in_flight)
+            gather = AsyncStatsGather(self.n, self.A, self.dev, depth=depth) if self.world > 1 else None
+            self.pipe = SearchPipeline(self.mcts, self.model, self.n, self.A, depth=depth, device=self.dev, gather=gather)
+        self.pipe_ticket = self.pipe.submit(CONST["frac"], self.noise, self.zeros_r, self.root_logits, self.legal_i,
+                                            self.root_hidden)
+        return self.pipe_ticket
+
+    def finish_pipeline(self):
+        """Drain the pipeline; returns (visits, values) of the last search and all ranks' statistics of it (or None)."""
+        self.pipe.drain()
+        visits, _ = self.pipe.stats(self.pipe_ticket)
+        return visits, (self.pipe.gathered(self.pipe_ticket) if self.pipe.gather is not None else None)
 
     def search_step(self):
         """Roots.prepare + run_multi + root statistics (+ the statistics all_gather, off the compute stream)."""
@@ -476,9 +498,22 @@ def run_ours(args):
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def time_searches(bench, steps, warm):
+    def time_searches(bench, steps, warm, piped=False):
         """CUDA-event time of `steps` searches of one SearchBench (barrier + synchronize on both sides, max over
-        ranks); the gather of the last search is inside the timed region."""
+        ranks); the gather of the last search is inside the timed region.  piped: through SearchPipeline with
+        `--in-flight` searches on their own streams (drained inside the timed region), else one search at a time."""
+        if piped:
+            for _ in range(max(warm, 3 * args.in_flight)):    # each slot: one eager search, one capture, one replay
+                bench.pipelined_step()
+            bench.finish_pipeline()
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                bench.pipelined_step()
+            visits, out = bench.finish_pipeline()             # host-blocking: every slot's search and gather is done
+            e1.record()
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1)), visits, out
         for _ in range(warm):
             bench.search_step()
         bench.finish()
@@ -502,8 +537,15 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)   # let nvidia-smi attach before the timed regions
     # ---- timed region 1: device-resident search ------------------------------------------------
-    ms_total, visits, gathered = time_searches(sb, K, W)
+    piped = args.in_flight > 1
+    ms_one, visits_one, _ = time_searches(sb, K, W)                  # one search at a time (the latency figure)
     sims_total = world * N * (S - 1) * K
+    value_one = sims_total / (ms_one * 1e-3)
+    if piped:
+        ms_total, visits, gathered = time_searches(sb, K, W, piped=True)
+        assert torch.equal(visits, visits_one), "a search in the pipeline must equal the same search run alone"
+    else:
+        ms_total, visits, gathered = time_searches(sb, K, W)
     value = sims_total / (ms_total * 1e-3)
     assert int(visits.sum().item()) == N * (S - 1), "search did not run the expected simulations"
     if gathered is not None:
@@ -516,7 +558,7 @@ def run_ours(args):
         wl_w = dict(wl, per_gpu=wl["total"], total=wl["total"] * world, scaling="weak")
         sbw = SearchBench(torch, args, wl_w, wl_w["per_gpu"], rank, world, dev, model)
         kw = max(K // 2, 3)
-        ms_w, _, _ = time_searches(sbw, kw, 3)
+        ms_w, _, _ = time_searches(sbw, kw, 3, piped=piped)
         weak = {"value": wl_w["total"] * (S - 1) * kw / (ms_w * 1e-3), "unit": "simulations/s", "trees_per_gpu": wl_w["per_gpu"],
                 "trees_total": wl_w["total"], "ms_per_step": ms_w / kw, "steps": kw}
         del sbw
@@ -555,18 +597,20 @@ def run_ours(args):
         barrier()
         return sims_total / (max_over_ranks(max(e0.elapsed_time(e1), 0.0)) * 1e-3)
 
-    e2e_serial = timed_e2e(e2e_step)
+    e2e_serial = timed_e2e(e2e_step, warm=6)   # new Roots per search alternate between two cached handles: eager, capture, replay each
     # the same work through the double-buffered public API: the copies of neighbouring searches overlap the search
-    pipe = SearchPipeline(mcts, model, N, A, depth=2, device=dev)
-    h_out = [(torch.empty(N, A, dtype=torch.int32).pin_memory(), torch.empty(N).pin_memory()) for _ in range(2)]
+    depth = max(args.in_flight, 2)
+    pipe = sb.pipe if (sb.pipe is not None and world == 1) else SearchPipeline(mcts, model, N, A, depth=depth, device=dev)
+    depth = pipe.depth
+    h_out = [(torch.empty(N, A, dtype=torch.int32).pin_memory(), torch.empty(N).pin_memory()) for _ in range(depth)]
     turn = [0]
 
     def piped_step():
-        hv, hval = h_out[turn[0] % 2]
+        hv, hval = h_out[turn[0] % depth]
         turn[0] += 1
         pipe.submit(CONST["frac"], h_noise, h_reward, h_logits, h_legal, h_hidden, hv, hval)
 
-    e2e_value = timed_e2e(piped_step, pipe.drain, warm=6)   # each slot: one eager search, one capture, one replay
+    e2e_value = timed_e2e(piped_step, pipe.drain, warm=3 * depth)   # each slot: one eager search, one capture, one replay
     assert int(h_out[0][0].sum().item()) == N * (S - 1) and torch.equal(h_out[0][0], h_out[1][0]), "pipelined search result"
     assert torch.equal(h_out[0][0], h_visits), "pipelined and serial searches must agree"
     h2d = sum(t.numel() * t.element_size() for t in (h_noise, h_logits, h_legal, h_hidden, h_reward))
@@ -648,19 +692,26 @@ def run_ours(args):
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl['name']}: {wl['total']} trees in total, {N} per GPU x {world} GPU(s) ({wl['scaling']} "
-                                   f"scaling), {S - 1} simulations executed per search (core/mcts.py:25-26), "
+                                   f"scaling), {S - 1} simulations executed per search (core/mcts.py:25-26), {max(args.in_flight, 1)} independent "
+                                   f"search(es) in flight per GPU on their own streams, "
                                    f"{'MuZeroNetFull' if wl['game'] == 'Hanabi-Full' else 'MuZeroNet'} random-init with re-drawn heads",
                        "baseline_config": wl["config"], "trees_per_gpu": N, "trees_total": wl["total"], "actions": A,
                        "simulations": S, "stack": args.stack, "mdp": wl["mdp"], "model_amp": args.amp,
                        "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
+                       "searches_in_flight": max(args.in_flight, 1),
                        "l2": f"per search the tree nodes ({nodes_mb:.0f} MB) + hidden pool ({pool_mb:.0f} MB) per GPU; the roofline "
                              "launches are timed with L2 flushed (256 MiB write) before each one"},
             "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "SearchPipeline.submit/wait (hanabizero_b200/mcts.py): pinned host inputs in, root statistics out, "
-                           "every search; two searches in flight so the copies overlap the neighbouring search",
+                           f"every search; {depth} searches in flight, each slot on its own compute stream, copies on two "
+                           "copy streams",
                     "serial": {"value": e2e_serial, "api": "Roots.prepare + MCTS.run_multi + get_stats on host tensors, one "
                                                            "search at a time, a stream synchronise per search"}},
-            "us_per_simulation": 1e3 * ms_total / K / (S - 1),
+            "one_search_at_a_time": {"value": value_one, "unit": "simulations/s", "ms_per_search": ms_one / K,
+                                     "us_per_simulation": 1e3 * ms_one / K / (S - 1),
+                                     "what": "the same K searches issued one after the other on one stream (the latency of "
+                                             "a search; `value` keeps several independent searches in flight)"},
+            "us_per_simulation": 1e3 * ms_one / K / (S - 1),
             "gpu_launches": int(launches_per_search * K),
             "gpu_launches_per_search": int(launches_per_search),
             "library_gemm_launches_per_search": int(gemm_per_search),

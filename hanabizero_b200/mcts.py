@@ -154,7 +154,12 @@ class MCTS(object):
         mm.clear()
         if sims < 2:
             return
-        ch = ws.chain = plan.chain(roots.root_num)   # referenced by the workspace: outlives an eviction from the plan's cache
+        if ws.chain is None or ws.chain.plan is not plan:
+            # the workspace owns its chain (activation buffers + cuBLASLt plan): searches of different tree batches may
+            # run on different streams at the same time (SearchPipeline), and a captured graph keeps its buffers alive
+            from .plan import BoundChain
+            ws.chain = BoundChain(plan, roots.root_num)
+        ch = ws.chain
         io = _lib.SearchIO()
         io.value_logits, io.ld_value = ptr(ch.value_logits), ch.value_logits.stride(0)
         io.reward_logits, io.ld_reward = ptr(ch.reward_logits), ch.reward_logits.stride(0)
@@ -234,38 +239,45 @@ def _flat(x):
 
 
 class SearchPipeline:
-    """Host-fed searches, double-buffered: while search i runs on the compute stream, the inputs of search i+1 are
-    copied in from pinned host memory on a copy stream and the root statistics of search i-1 are copied out.
-    Each slot owns its tree batch (and therefore its captured search graph) and its device staging buffers, so
-    consecutive searches never share memory; `depth` searches can be in flight.
+    """Searches kept in flight: `depth` slots, each with its own tree batch (and therefore its own captured search
+    graph, network buffers and staging buffers) and its own compute stream.  Inputs are copied in on a copy stream and
+    root statistics copied out on another, so for host-fed searches the copies of search i+1 / i-1 overlap search i —
+    and, because a search is a dependent chain of short launches that leaves the GPU idle at every kernel boundary, the
+    searches of different slots overlap each other: independent root batches (the reference's actors, each with its
+    own p_mcts_num roots, core/selfplay_worker.py:93,102) fill one another's bubbles.
 
         pipe = SearchPipeline(MCTS(cfg), model, num_roots, num_actions)
         t = pipe.submit(fraction, noises, rewards, logits, legal, hidden_roots, out_visits, out_values)   # returns at once
         ...
-        pipe.wait(t)          # out_visits / out_values (pinned host tensors) now hold the result of that search
+        pipe.wait(t)          # out_visits / out_values now hold the result of that search
 
-    Inputs are what Roots.prepare + MCTS.run_multi take (core/selfplay_worker.py:276-283), as pinned host tensors
-    (pageable memory works but serialises the copies); `noises=None` selects prepare_no_noise."""
+    Inputs are what Roots.prepare + MCTS.run_multi take (core/selfplay_worker.py:276-283): pinned host tensors
+    (pageable memory works but serialises the copies) or device tensors; outputs likewise.  `noises=None` selects
+    prepare_no_noise.  `gather` (dist.AsyncStatsGather with depth >= this depth) additionally all-gathers every
+    search's statistics over the ranks, off the compute streams; `gathered(t)` returns them.
+    Weights must not change while searches are in flight: call drain() before updating the module."""
 
-    def __init__(self, mcts, model, num_roots, num_actions, depth=2, device=None):
+    def __init__(self, mcts, model, num_roots, num_actions, depth=4, device=None, gather=None):
         self.mcts, self.model = mcts, model
         self.n, self.a, self.depth = int(num_roots), int(num_actions), int(depth)
         self.device = next(model.parameters()).device if device is None else torch.device(device)
         dev, sims = self.device, int(mcts.config.num_simulations)
-        self.compute = torch.cuda.current_stream(dev)
+        if gather is not None and gather.depth < self.depth:
+            raise ValueError("gather.depth must be at least the pipeline depth")
+        self.gather = gather
         self.copy_in, self.copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.slots = []
         for _ in range(self.depth):
             self.slots.append(dict(
-                roots=cytree.Roots(self.n, self.a, sims, device=dev),
+                roots=cytree.Roots(self.n, self.a, sims, device=dev), stream=torch.cuda.Stream(dev),
                 noise=torch.empty(self.n, self.a, device=dev), reward=torch.empty(self.n, device=dev),
                 logits=torch.empty(self.n, self.a, device=dev), legal=torch.empty(self.n, self.a, dtype=torch.int32, device=dev),
                 hidden=None, visits=torch.empty(self.n, self.a, dtype=torch.int32, device=dev),
-                values=torch.empty(self.n, device=dev),
+                values=torch.empty(self.n, device=dev), ticket=None,
                 ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False))
         self._next = 0
 
-    def submit(self, fraction, noises, rewards, logits, legal, hidden_roots, out_visits, out_values):
+    def submit(self, fraction, noises, rewards, logits, legal, hidden_roots, out_visits=None, out_values=None):
         i = self._next
         self._next = (i + 1) % self.depth
         s = self.slots[i]
@@ -275,6 +287,8 @@ class SearchPipeline:
         hidden_roots = torch.as_tensor(hidden_roots)
         if s["hidden"] is None or s["hidden"].shape != hidden_roots.shape or s["hidden"].dtype != hidden_roots.dtype:
             s["hidden"] = torch.empty(hidden_roots.shape, dtype=hidden_roots.dtype, device=self.device)
+        caller = torch.cuda.current_stream(self.device)
+        self.copy_in.wait_stream(caller)       # device-resident inputs: whatever produced them on the caller's stream
         with torch.cuda.stream(self.copy_in):
             # the slot's staging buffers were last read by its previous search, which ev_out (waited above) follows
             if noises is not None:
@@ -284,28 +298,47 @@ class SearchPipeline:
             s["legal"].copy_(torch.as_tensor(legal), non_blocking=True)
             s["hidden"].copy_(hidden_roots, non_blocking=True)
             s["ev_in"].record(self.copy_in)
-        self.compute.wait_event(s["ev_in"])
-        with torch.cuda.stream(self.compute):
+        compute = s["stream"]
+        compute.wait_event(s["ev_in"])
+        with torch.cuda.stream(compute):
             if noises is not None:
                 s["roots"].prepare(fraction, s["noise"], s["reward"], s["logits"], s["legal"])
             else:
                 s["roots"].prepare_no_noise(s["reward"], s["logits"], s["legal"])
             self.mcts.run_multi(s["roots"], self.model, s["hidden"])
-            check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, self.compute.cuda_stream, ptr(s["visits"]),
+            check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, compute.cuda_stream, ptr(s["visits"]),
                                                       ptr(s["values"])))
-            s["ev_done"].record(self.compute)
+            s["ev_done"].record(compute)
+            if self.gather is not None:
+                s["ticket"] = self.gather.submit(s["visits"], s["values"])
         self.copy_out.wait_event(s["ev_done"])
         with torch.cuda.stream(self.copy_out):
-            out_visits.copy_(s["visits"], non_blocking=True)
-            out_values.copy_(s["values"], non_blocking=True)
+            if out_visits is not None:
+                out_visits.copy_(s["visits"], non_blocking=True)
+            if out_values is not None:
+                out_values.copy_(s["values"], non_blocking=True)
             s["ev_out"].record(self.copy_out)
         return i
 
     def wait(self, ticket):
         self.slots[ticket]["ev_out"].synchronize()
 
+    def stats(self, ticket):
+        """Device tensors (visits int32 [n, A], values float32 [n]) of a ticket's search; valid until the slot is
+        submitted again.  The current stream waits for the search."""
+        s = self.slots[ticket]
+        torch.cuda.current_stream(self.device).wait_event(s["ev_done"])
+        return s["visits"], s["values"]
+
+    def gathered(self, ticket):
+        """All ranks' statistics of a ticket's search (needs `gather`); the current stream waits for the collective."""
+        return self.gather.result(self.slots[ticket]["ticket"])
+
     def drain(self):
         for s in self.slots:
             if s["busy"]:
                 s["ev_out"].synchronize()
+                s["stream"].synchronize()
                 s["busy"] = False
+        if self.gather is not None and self.gather.stream is not None:
+            self.gather.stream.synchronize()

@@ -222,29 +222,36 @@ def test_plan_and_module_paths_select_the_same_actions():
     assert agree > 0.9    # same function up to float rounding of the network; the trees see ~1e-6 different inputs
 
 
-def test_search_pipeline_equals_serial_searches():
-    """SearchPipeline (double-buffered host-fed searches on separate copy streams) must return, for every submitted
-    search, exactly what a stand-alone Roots.prepare + run_multi returns for the same inputs — including when the
-    inputs change from search to search and when a slot is reused."""
+@pytest.mark.parametrize("depth,on_device", [(2, False), (3, False), (3, True)])
+def test_search_pipeline_equals_serial_searches(depth, on_device):
+    """SearchPipeline (searches of several slots in flight on their own compute streams, inputs and results moved on
+    copy streams) must return, for every submitted search, exactly what a stand-alone Roots.prepare + run_multi returns
+    for the same inputs — including when the inputs change from search to search, when a slot is reused (eager search,
+    graph capture, replays) and when inputs / outputs are device tensors."""
     from hanabizero_b200 import cytree
     from hanabizero_b200.mcts import MCTS, SearchPipeline
     dev, model, logits, hidden, legal, noise, cfg, a = _setup("torch_amp")
     rng = np.random.default_rng(11)
     mcts = MCTS(cfg)
-    pipe = SearchPipeline(mcts, model, N, a, depth=2)
-    pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+    pipe = SearchPipeline(mcts, model, N, a, depth=depth)
+    if on_device:
+        pin = lambda t: t.detach().to(dev).contiguous()
+        out = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device=dev)
+    else:
+        pin = lambda t: t.detach().cpu().contiguous().pin_memory()
+        out = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype).pin_memory()
     jobs = []
-    for k in range(6):
+    for k in range(4 * depth):
         nz = torch.from_numpy(rng.dirichlet([0.3] * a, N).astype(np.float32))
         lg = logits.float().cpu() + 0.1 * k
         hd = hidden.cpu() * (1.0 + 0.01 * k)
         jobs.append(dict(noise=pin(nz) if k % 3 else None, reward=pin(torch.zeros(N)), logits=pin(lg), legal=pin(legal.int()),
-                         hidden=pin(hd), visits=torch.empty(N, a, dtype=torch.int32).pin_memory(),
-                         values=torch.empty(N).pin_memory()))
+                         hidden=pin(hd), visits=out(N, a, dtype=torch.int32), values=out(N)))
     tickets = [pipe.submit(0.25, j["noise"], j["reward"], j["logits"], j["legal"], j["hidden"], j["visits"], j["values"])
                for j in jobs]
     pipe.drain()
-    assert tickets == [0, 1, 0, 1, 0, 1]
+    torch.cuda.synchronize()
+    assert tickets == [k % depth for k in range(4 * depth)]
     ref = MCTS(cfg)
     for j in jobs:
         roots = cytree.Roots(N, a, S)
@@ -254,5 +261,5 @@ def test_search_pipeline_equals_serial_searches():
             roots.prepare(0.25, j["noise"], j["reward"], j["logits"], j["legal"])
         ref.run_multi(roots, model, j["hidden"])
         v, val = roots.get_stats_tensors()
-        assert torch.equal(v.cpu(), j["visits"]) and torch.equal(val.cpu(), j["values"])
+        assert torch.equal(v.cpu(), j["visits"].cpu()) and torch.equal(val.cpu(), j["values"].cpu())
         assert int(j["visits"].sum()) == N * (S - 1)
