@@ -791,38 +791,38 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
         shifts = np.arange(A, dtype=np.uint32)
         for gi in range(G):
             pipe.observe_now(gi)
-        warm = threading.Barrier(G + 1)
         errors = []
+
+        def one_step(gi, step):
+            obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
+            if fmt == "bits":
+                rows = leg                                  # meta rows [n, 4]: word 0 is the legal mask
+            else:                                           # 0/1 rows -> the same mask word
+                rows = rows_tmp[gi]
+                rows[:, 0] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
+            halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
+            pipe.step(gi)
+
+        for step in range(5):             # warm-up on this thread: a stream capture must not race another thread's calls
+            for gi in range(G):
+                one_step(gi, step)
+        start = threading.Barrier(G + 1)
 
         def drive(gi):
             try:
                 torch.cuda.set_device(dev)
-                for step in range(5 + T_host):
-                    if step == 5:
-                        warm.wait()      # main thread: barrier + start event
-                        warm.wait()
-                    obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
-                    if fmt == "bits":
-                        rows = leg                                  # meta rows [n, 4]: word 0 is the legal mask
-                    else:                                           # 0/1 rows -> the same mask word
-                        rows = rows_tmp[gi]
-                        rows[:, 0] = torch.from_numpy((leg.numpy().astype(np.uint32) << shifts).sum(1, dtype=np.uint32).view(np.int32))
-                    halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
-                    pipe.step(gi)
+                start.wait()
+                for step in range(5, 5 + T_host):
+                    one_step(gi, step)
             except Exception as exc:      # surfaced by the main thread
                 errors.append(exc)
-                try:
-                    warm.abort()
-                except Exception:
-                    pass
 
         threads = [threading.Thread(target=drive, args=(gi,), daemon=True) for gi in range(G)]
         for th in threads:
             th.start()
-        warm.wait()
         barrier()
         e0.record()
-        warm.wait()
+        start.wait()
         for th in threads:
             th.join()
         if errors:
