@@ -636,28 +636,41 @@ def run_ours(args):
     if not args.quick:
         env_obj = bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, rank, world, dev)
         # ---- whole self-play moves, device-resident ----
-        from hanabizero_b200.selfplay import SelfPlayEngine
-        eng = SelfPlayEngine(N, wl["game"], model, cfg, seeds=np.arange(N) + 7 * N * (rank + 1), mdp=wl["mdp"],
-                             stack=args.stack, device=dev)
-        eng.reset()
-        for _ in range(3):
-            eng.step()
-        barrier()
-        e0.record()
-        n_moves = 5
-        for _ in range(n_moves):
-            eng.step()
-        e1.record()
-        barrier()
-        sp_ms = max_over_ranks(e0.elapsed_time(e1))
-        eng.env.check()
-        selfplay_moves = world * N * n_moves / (sp_ms * 1e-3)
+        from hanabizero_b200.selfplay import SelfPlayEngine, SelfPlayPool
+        E = max(args.in_flight, 1)      # engines (actors) per GPU, each with its own N games, on its own stream
+
+        def timed_selfplay(engines, n_moves=5):
+            pool = SelfPlayPool(engines)
+            pool.reset()
+            for _ in range(3):          # eager search, capture, replay
+                pool.step()
+            pool.synchronize()
+            barrier()
+            e0.record()
+            for _ in range(n_moves):
+                pool.step()
+            pool.synchronize()
+            e1.record()
+            barrier()
+            for eng in engines:
+                eng.env.check()
+            return world * len(engines) * N * n_moves / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
+
+        make = lambda e: SelfPlayEngine(N, wl["game"], model, cfg, seeds=np.arange(N) + 7 * N * (rank * E + e + 1), mdp=wl["mdp"],
+                                        stack=args.stack, device=dev, game_offset=(rank * E + e) * N)
+        engines = [make(e) for e in range(E)]
+        one_moves = timed_selfplay(engines[:1])
+        selfplay_moves = timed_selfplay(engines) if E > 1 else one_moves
         selfplay_obj = {"metric": "selfplay_moves_per_sec", "value": selfplay_moves, "unit": "moves/s",
                         "what": "frame stack -> representation+prediction -> Roots.prepare(Dirichlet) -> run_multi -> "
-                                "select_action -> env step with auto-reset, all on the device (SelfPlayEngine.step)",
+                                f"select_action -> env step with auto-reset, all on the device; {E} engines (actors) of {N} games "
+                                "each, every engine on its own stream (SelfPlayPool.step)",
+                        "engines": E,
                         "simulations_per_sec": selfplay_moves * (S - 1),
-                        "fraction_of_search_only": selfplay_moves * (S - 1) / value}
-        del eng
+                        "fraction_of_search_only": selfplay_moves * (S - 1) / value,
+                        "one_engine": {"value": one_moves, "simulations_per_sec": one_moves * (S - 1),
+                                       "fraction_of_one_search_at_a_time": one_moves * (S - 1) / value_one}}
+        del engines
     clocks = sampler.stop() if rank == 0 else None
 
     roof = tree_roofline(torch, args, wl, sb, model, lib) if rank == 0 else None
@@ -783,10 +796,10 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
     # nanoseconds per game in C; numpy needs ~15 vectorised passes = more than the whole device step)
     rows_tmp = [torch.zeros(n_g, 4, dtype=torch.int32) for _ in range(G)]
 
-    def timed_pipeline(fmt):
+    def timed_pipeline(fmt, zero_copy=None):
         """One host thread per half-batch (the ctypes calls and the graph launches release the GIL): each thread loops
         wait -> pick -> step on its own group, so one half's host work overlaps the other half's device work."""
-        pipe = EnvPipeline(halves, fmt=fmt)
+        pipe = EnvPipeline(halves, fmt=fmt, zero_copy=zero_copy)
         h_acts = [pipe.actions(gi) for gi in range(G)]          # the pipeline's own pinned action buffers
         shifts = np.arange(A, dtype=np.uint32)
         for gi in range(G):
@@ -834,6 +847,7 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
         return v, pipe.d2h_bytes_per_step
 
     e2e_bits, d2h_bits = timed_pipeline("bits")
+    e2e_staged, _ = timed_pipeline("bits", zero_copy=False)
     e2e_u8, d2h_u8 = timed_pipeline("u8")
     e2e_f32, d2h_f32 = timed_pipeline("f32")
     for h in halves:
@@ -882,11 +896,14 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
                           "steps_per_s_by_games_per_gpu": sat},
             "e2e": {"value": e2e_bits, "unit": "steps/s", "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": d2h_bits,
                     "obs_format": "bits",
-                    "what": "EnvPipeline (hanabizero_b200/hanabi_env.py): actions from pinned host memory in, the global "
-                            "observation as a bit string (785 bits -> 100 bytes per game, hz_envs_step_observe_bits) + legal "
-                            "mask + reward/done/score out to pinned host memory every step, the host picks the next action "
-                            "from the returned mask (hz_host_random_legal); two half-batches in flight on two streams, each "
-                            "half-step one CUDA graph launch, one host thread per half",
+                    "what": "EnvPipeline (hanabizero_b200/hanabi_env.py): actions in pinned host memory in, the global "
+                            "observation as a bit string (785 bits -> 100 bytes per game) + legal mask + reward/done/score out "
+                            "to pinned host memory every step, the host picks the next action from the returned mask "
+                            "(hz_host_random_legal); no staging copies: the kernel reads the actions from and writes the rows "
+                            "to the pinned buffers itself (hz_envs_host_step, one launch + one event record per half-step); two "
+                            "half-batches in flight on two streams, one host thread per half",
+                    "bits_staged": {"value": e2e_staged, "what": "the same rows through device staging buffers: H2D copy, "
+                                                                  "kernel, two D2H copies, replayed as one CUDA graph"},
                     "u8": {"value": e2e_u8, "d2h_bytes_per_step": d2h_u8},
                     "f32": {"value": e2e_f32, "d2h_bytes_per_step": d2h_f32}},
             "scalar_dropin_steps_per_s": scalar,

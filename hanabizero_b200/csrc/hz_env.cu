@@ -668,6 +668,7 @@ struct hz_envs {
   int32_t* err = nullptr;
   bool started = false;
   int dump_len = 0;
+  cudaEvent_t host_done = nullptr;   // completion of the last hz_envs_host_step (created on first use)
   EnvView view() const { return EnvView{state, mt, mti, err, N, g}; }
 };
 
@@ -737,6 +738,7 @@ int hz_envs_destroy(hz_envs* e) {
   if (!e) return HZ_OK;
   DeviceGuard dg(e->device);
   cudaFree(e->state); cudaFree(e->mt); cudaFree(e->mti); cudaFree(e->err);
+  if (e->host_done) cudaEventDestroy(e->host_done);
   delete e;
   return HZ_OK;
 }
@@ -849,6 +851,43 @@ int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, 
   a.out_bits = out_bits; a.ld_bits = ld_bits; a.out_meta = out_meta;
   if (actions) return launch_env<false, true, true>(e, (cudaStream_t)stream, a);
   return launch_env<false, false, true>(e, (cudaStream_t)stream, a);   // actions == NULL: observe only
+}
+
+// Host-facing step without staging copies.  Pinned (page-locked) host memory is device-addressable under unified
+// addressing, so the kernel reads the actions from, and writes the packed rows to, the caller's host buffers itself:
+// 116 bytes per game cross PCIe as posted writes from the SMs, and a step is ONE launch plus an event record instead
+// of copy -> kernel -> copy -> copy.  hz_envs_host_wait blocks the calling host thread until that step's rows are in
+// host memory (kernel completion flushes the writes).
+int hz_envs_host_step(hz_envs* e, void* stream, const int32_t* h_actions, int auto_reset, uint32_t* h_bits,
+                      int64_t ld_words, uint32_t* h_meta) {
+  if (!e || !h_bits) { set_error("hz_envs_host_step: NULL argument"); return HZ_ERR_ARG; }
+  DeviceGuard dg(e->device);
+  const void* ptrs[3] = {h_actions, h_bits, h_meta};
+  for (const void* p : ptrs) {
+    if (!p) continue;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess || (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged &&
+                                                            at.type != cudaMemoryTypeDevice)) {
+      cudaGetLastError();
+      set_error("hz_envs_host_step: buffers must be page-locked host memory (torch .pin_memory(), cudaHostAlloc)");
+      return HZ_ERR_ARG;
+    }
+  }
+  if (!e->host_done && cudaEventCreateWithFlags(&e->host_done, cudaEventDisableTiming) != cudaSuccess) {
+    return fail_cuda(cudaGetLastError(), "hz_envs_host_step: event");
+  }
+  if (int rc = hz_envs_step_observe_bits(e, stream, h_actions, nullptr, auto_reset, h_bits, ld_words, h_meta)) return rc;
+  const cudaError_t ce = cudaEventRecord(e->host_done, (cudaStream_t)stream);
+  if (ce != cudaSuccess) return fail_cuda(ce, "hz_envs_host_step: record");
+  return HZ_OK;
+}
+
+int hz_envs_host_wait(hz_envs* e) {
+  if (!e) { set_error("hz_envs_host_wait: NULL handle"); return HZ_ERR_ARG; }
+  if (!e->host_done) return HZ_OK;   // nothing submitted yet
+  const cudaError_t ce = cudaEventSynchronize(e->host_done);
+  if (ce != cudaSuccess) return fail_cuda(ce, "hz_envs_host_wait");
+  return HZ_OK;
 }
 
 namespace {

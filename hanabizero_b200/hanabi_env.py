@@ -205,13 +205,20 @@ class EnvPipeline:
 
     fmt: "bits" = packed (HanabiVecEnv.step_bits / unpack_bits; `wait` returns (observation words int32 [n, W],
     meta int32 [n, 4] = {legal mask, reward, done, score})); "u8" / "f32" = (global observation [n, D], legal [n, A])
-    as 0/1 bytes or float32 — what round 1 shipped, kept for comparison (8x / 32x the bytes)."""
+    as 0/1 bytes or float32 — what round 1 shipped, kept for comparison (8x / 32x the bytes).
 
-    def __init__(self, envs, fmt="bits", use_graphs=True):
+    zero_copy (fmt="bits" only, default): no staging copies at all — the kernel reads the actions from and writes the
+    packed rows to the pinned host buffers itself (hz_envs_host_step: one launch + one event record per step, two
+    ctypes calls and no torch call on the host side of a step)."""
+
+    def __init__(self, envs, fmt="bits", use_graphs=True, zero_copy=None):
         if fmt not in ("bits", "u8", "f32"):
             raise ValueError("fmt must be 'bits', 'u8' or 'f32'")
         self.envs = list(envs) if isinstance(envs, (list, tuple)) else [envs]
         self.fmt, self.groups, self.use_graphs = fmt, len(self.envs), bool(use_graphs)
+        self.zero_copy = (fmt == "bits") if zero_copy is None else bool(zero_copy)
+        if self.zero_copy and fmt != "bits":
+            raise ValueError("zero_copy needs fmt='bits'")
         self.slots = []
         self.d2h_bytes_per_step = 0
         for env in self.envs:
@@ -256,9 +263,16 @@ class EnvPipeline:
         if s["h_leg"] is not None:
             s["h_leg"].copy_(s["d_leg"], non_blocking=True)
 
+    def _host_step(self, s, with_actions):
+        env = s["env"]
+        check(env._lib.hz_envs_host_step(env._h, s["stream"].cuda_stream, s["h_act"].data_ptr() if with_actions else None, 1,
+                                         s["h_obs"].data_ptr(), s["h_obs"].stride(0), s["h_leg"].data_ptr()))
+
     def observe_now(self, group):
         """Current observation of the group's games (no step)."""
         s = self.slots[group]
+        if self.zero_copy:
+            return self._host_step(s, False)
         with torch.cuda.stream(s["stream"]):
             self._enqueue(s, False)
             s["done"].record(s["stream"])
@@ -271,6 +285,9 @@ class EnvPipeline:
         s = self.slots[group]
         if h_actions is not None and h_actions.data_ptr() != s["h_act"].data_ptr():
             s["h_act"].copy_(h_actions)
+        if self.zero_copy:
+            s["steps"] += 1
+            return self._host_step(s, True)
         with torch.cuda.stream(s["stream"]):
             if s["graph"] is None and s["steps"] >= 2 and self.use_graphs:
                 s["stream"].synchronize()
@@ -290,12 +307,18 @@ class EnvPipeline:
         """Block until the group's last submission is in host memory; returns (observation rows, legal) host tensors —
         for fmt="bits": (observation words [n, W] int32, meta [n, 4] int32 = {legal mask, reward, done, score})."""
         s = self.slots[group]
-        s["done"].synchronize()
+        if self.zero_copy:
+            check(s["env"]._lib.hz_envs_host_wait(s["env"]._h))
+        else:
+            s["done"].synchronize()
         return s["h_obs"], s["h_leg"]
 
     def drain(self):
         for s in self.slots:
-            s["done"].synchronize()
+            if self.zero_copy:
+                check(s["env"]._lib.hz_envs_host_wait(s["env"]._h))
+            else:
+                s["done"].synchronize()
             torch.cuda.current_stream(s["env"].device).wait_stream(s["stream"])
 
 

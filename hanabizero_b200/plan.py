@@ -17,6 +17,7 @@ Weights live in fixed buffers that `refresh()` rewrites in place whenever the mo
 change, so chains and CUDA graphs built over a plan stay valid across training updates.
 """
 import ctypes as C
+import weakref
 
 import torch
 
@@ -327,10 +328,13 @@ class InitialPlan:
         self._sig = sig
         return True
 
-    def bound(self, n):
-        """Static buffers + GEMM chain for batch size n (cached; `x` is the input buffer hz_ring_gather fills)."""
-        b = self._bound.get(n)
-        if b is not None:
+    def bound(self, n, owner=None):
+        """Static buffers + GEMM chain for batch size n (cached per (n, owner); `x` is the input buffer hz_ring_gather
+        fills).  Callers that may run at the same time on different streams (the engines of a SelfPlayPool) pass
+        themselves as `owner` and get buffers of their own."""
+        key = (n, None if owner is None else id(owner))
+        b = self._bound.get(key)
+        if b is not None and (owner is None or b.owner() is owner):
             return b
         dev, dt, w = self.device, self.dtype, self._w
         F, H, P3 = self.F, self.H, self.P3
@@ -378,16 +382,17 @@ class InitialPlan:
         arr = (GemmStep * b.n_steps)(*steps)
         b.handle = C.c_void_p()
         check(self.lib.hz_gemm_plan_create(C.byref(b.handle), dev.index, b.x.element_size(), arr, b.n_steps))
-        if len(self._bound) >= 4:
+        b.owner = (lambda: None) if owner is None else weakref.ref(owner)
+        if len(self._bound) >= 16:
             self._bound.pop(next(iter(self._bound)))   # buffers stay alive while a caller holds the object
-        self._bound[n] = b
+        self._bound[key] = b
         return b
 
     @torch.no_grad()
-    def run(self, n, decode_value=False):
-        """Runs the chain on bound(n).x (already filled).  Returns (value [n] or None, policy_logits [n, A] float32,
-        hidden_state [n, F] plan dtype) — views of the plan's buffers, valid until the next run."""
-        b = self.bound(n)
+    def run(self, n, decode_value=False, owner=None):
+        """Runs the chain on bound(n, owner).x (already filled).  Returns (value [n] or None, policy_logits [n, A]
+        float32, hidden_state [n, F] plan dtype) — views of the plan's buffers, valid until the next run."""
+        b = self.bound(n, owner)
         st = torch.cuda.current_stream(self.device).cuda_stream
         check(self.lib.hz_gemm_plan_run(b.handle, st, 0, b.n_steps))
         value = None

@@ -113,6 +113,7 @@ class SelfPlayEngine:
         self.alpha = float(getattr(config, "root_dirichlet_alpha", 0.3))
         self.noise_seed, self.game_offset, self.moves = int(noise_seed), int(game_offset), 0
         self.recorder = None
+        self._roots = None
         if record:
             from .trajectory import TrajectoryRecorder
             self.recorder = TrajectoryRecorder(num_games, self.obs_dim, self.env.num_actions, self.stack,
@@ -174,14 +175,18 @@ class SelfPlayEngine:
         if self.iplan is not None:
             self.model.eval()
             self.iplan.refresh()
-            b = self.iplan.bound(n)
+            b = self.iplan.bound(n, owner=self)
             check(self.lib.hz_ring_gather(self._stream(), ptr(self.ring), self.head, ptr(b.x), b.x.stride(0), self.Dp, n,
                                           self.stack, self.Dp, b.x.element_size()))
-            _, logits, hidden = self.iplan.run(n)
+            _, logits, hidden = self.iplan.run(n, owner=self)
         else:
             with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
                 _, logits, hidden = self.model.initial_inference_device(self.frames.view(n, -1))
-        roots = cytree.Roots(n, self.env.num_actions, cfg.num_simulations, device=self.dev)
+        # one tree batch per engine, prepared anew every move: its handle (and the search graph captured over it) is
+        # never shared with another engine, whose searches may be in flight on another stream (SelfPlayPool)
+        if self._roots is None or self._roots.tree_nodes != int(cfg.num_simulations):
+            self._roots = cytree.Roots(n, self.env.num_actions, cfg.num_simulations, device=self.dev)
+        roots = self._roots
         zeros = torch.zeros(n, device=self.dev)
         legal_i = self.legal.int()
         if noise:   # np.random.dirichlet([alpha] * A) per root (selfplay_worker.py:279), drawn on the device
@@ -228,6 +233,43 @@ class SelfPlayEngine:
         self._push(out["done"])
         self.recorder.begin(self._obs, self.legal, mask=out["done"])
         return out
+
+
+class SelfPlayPool:
+    """Several SelfPlayEngines — disjoint game batches, the reference's actors (core/selfplay_worker.py:93-102: each
+    DataWorker owns p_mcts_num games) — stepped round-robin, each on its own CUDA stream.  A move is a dependent chain
+    of short launches (root inference, search, action pick, env step), so one engine leaves most of the GPU idle; the
+    engines' chains interleave and fill one another's gaps.  Nothing here synchronises with the host."""
+
+    def __init__(self, engines):
+        self.engines = list(engines)
+        if not self.engines:
+            raise ValueError("SelfPlayPool needs at least one engine")
+        dev = self.engines[0].dev
+        self.streams = [torch.cuda.Stream(dev) for _ in self.engines]
+        cur = torch.cuda.current_stream(dev)
+        for s in self.streams:
+            s.wait_stream(cur)       # engine construction ran on the caller's stream
+
+    def reset(self):
+        out = []
+        for eng, s in zip(self.engines, self.streams):
+            with torch.cuda.stream(s):
+                out.append(eng.reset())
+        return out
+
+    def step(self, **kw):
+        """One move of every engine; returns the engines' result dicts (CUDA tensors, each valid on its engine's
+        stream: call synchronize() — or make your stream wait — before reading them elsewhere)."""
+        out = []
+        for eng, s in zip(self.engines, self.streams):
+            with torch.cuda.stream(s):
+                out.append(eng.step(**kw))
+        return out
+
+    def synchronize(self):
+        for s in self.streams:
+            s.synchronize()
 
 
 @torch.no_grad()

@@ -226,6 +226,15 @@ int hz_envs_step_observe_u8(hz_envs* e, void* stream, const int32_t* actions, co
  * per game instead of one word out of every 116-byte row. */
 int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, const uint8_t* active, int auto_reset,
                               uint32_t* out_bits, int64_t ld_words, uint32_t* out_meta);
+/* Host-facing step for callers that keep actions and results in page-locked HOST memory (a vectorised stand-in for
+ * the per-step pyhanabi.h calls of HanabiEnv.step, rl_env.py:292-442): h_actions (int32[N], NULL = observe only),
+ * h_bits / h_meta as in hz_envs_step_observe_bits but HOST pointers.  No staging copies: pinned memory is
+ * device-addressable, the kernel reads and writes it directly, so a step is one launch + one event record on
+ * `stream`.  hz_envs_host_wait blocks the calling thread until the last hz_envs_host_step of this handle has landed in
+ * host memory.  Neither call holds any lock: one host thread per game batch may drive its own handle. */
+int hz_envs_host_step(hz_envs* e, void* stream, const int32_t* h_actions, int auto_reset, uint32_t* h_bits,
+                      int64_t ld_words, uint32_t* h_meta);
+int hz_envs_host_wait(hz_envs* e);
 /* HOST helper for callers that drive the games from the CPU through the packed rows (no device work): a uniformly
  * random legal move per game from word `legal_word` (= W) of each host row, counter-based (seed, game, step). */
 int hz_host_random_legal(const uint32_t* rows, int64_t ld_words, int legal_word, int num_games, int num_actions,

@@ -234,10 +234,11 @@ def test_bit_packed_rows_equal_float_observations(name):
     p_env.check()
 
 
-@pytest.mark.parametrize("fmt", ["bits", "u8", "f32"])
-def test_env_pipeline_matches_direct_stepping(fmt):
+@pytest.mark.parametrize("fmt,zero_copy", [("bits", True), ("bits", False), ("u8", False), ("f32", False)])
+def test_env_pipeline_matches_direct_stepping(fmt, zero_copy):
     """EnvPipeline (two groups, each on its own stream: pinned host actions in, kernel, result out) plays exactly the
-    games a plain step loop plays."""
+    games a plain step loop plays — with staging copies, and with the kernel reading / writing the pinned host buffers
+    itself (hz_envs_host_step)."""
     from hanabizero_b200.hanabi_env import EnvPipeline, HanabiVecEnv
     n, T, G = 48, 40, 2
     seeds = [np.arange(n) + 7 + 1000 * g for g in range(G)]
@@ -250,7 +251,7 @@ def test_env_pipeline_matches_direct_stepping(fmt):
         ref_g.append(g0.clone())
         ref_l.append(l0.clone())
         e.reset_all(observe=False)
-    pipe = EnvPipeline(envs, fmt=fmt)
+    pipe = EnvPipeline(envs, fmt=fmt, zero_copy=zero_copy)
     h_act = [torch.zeros(n, dtype=torch.int32).pin_memory() for _ in range(G)]
     for g in range(G):
         pipe.observe_now(g)

@@ -212,3 +212,36 @@ def test_initial_plan_matches_the_module(small):
         torch.testing.assert_close(st.float(), state.float(), rtol=tol, atol=tol)
         torch.testing.assert_close(lg, logits, rtol=tol, atol=tol)
         torch.testing.assert_close(v, value, rtol=10 * tol, atol=10 * tol)
+
+
+def test_selfplay_pool_equals_its_engines_stepped_alone():
+    """SelfPlayPool steps several engines on their own streams (their move chains interleave on the GPU); every engine
+    must play exactly the moves it plays when it is stepped alone: same actions, rewards, visit counts, scores."""
+    from hanabizero_b200.mcts import SearchConfig
+    from hanabizero_b200.model import MuZeroNetFull
+    from hanabizero_b200.selfplay import SelfPlayEngine, SelfPlayPool
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    N, A, S, E, moves = 48, 20, 10, 3, 5
+    model = MuZeroNetFull(785 * 4, A).randomize_heads().to(dev).eval()
+    cfg = SearchConfig(num_simulations=S, amp_type="torch_amp")
+    make = lambda e: SelfPlayEngine(N, "Hanabi-Full", model, cfg, seeds=np.arange(N) + 1000 * e, noise_seed=5,
+                                    game_offset=e * N, device=dev)
+    alone = []
+    for e in range(E):
+        eng = make(e)
+        eng.reset()
+        alone.append([{k: v.clone() for k, v in eng.step(deterministic=True).items()} for _ in range(moves)])
+    torch.cuda.synchronize()
+    pool = SelfPlayPool([make(e) for e in range(E)])
+    pool.reset()
+    together = []
+    for _ in range(moves):
+        outs = pool.step(deterministic=True)     # arg-max moves: sampled ones draw from torch's global generator
+        pool.synchronize()            # the result tensors live on the engines' streams: read them once those are done
+        together.append([{k: v.clone() for k, v in out.items()} for out in outs])
+    for m in range(moves):
+        outs = together[m]
+        for e in range(E):
+            for k in ("action", "reward", "done", "score", "visits", "root_value"):
+                assert torch.equal(outs[e][k], alone[e][m][k]), (m, e, k)
