@@ -797,15 +797,13 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
     rows_tmp = [torch.zeros(n_g, 4, dtype=torch.int32) for _ in range(G)]
 
     def timed_pipeline(fmt, zero_copy=None):
-        """One host thread per half-batch (the ctypes calls and the graph launches release the GIL): each thread loops
-        wait -> pick -> step on its own group, so one half's host work overlaps the other half's device work."""
+        """wait -> pick -> step, round-robin over the half-batches: while the host handles one half, the other half's
+        kernel (and its PCIe traffic) is in flight."""
         pipe = EnvPipeline(halves, fmt=fmt, zero_copy=zero_copy)
         h_acts = [pipe.actions(gi) for gi in range(G)]          # the pipeline's own pinned action buffers
         shifts = np.arange(A, dtype=np.uint32)
         for gi in range(G):
             pipe.observe_now(gi)
-        errors = []
-
         def one_step(gi, step):
             obs, leg = pipe.wait(gi)                      # pinned host views of the group's previous step
             if fmt == "bits":
@@ -816,30 +814,14 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
             halves[gi].random_legal_host(rows, h_acts[gi], seed=rank, step=step)
             pipe.step(gi)
 
-        for step in range(5):             # warm-up on this thread: a stream capture must not race another thread's calls
+        for step in range(5):             # warm-up (the staged variants capture their graphs here)
             for gi in range(G):
                 one_step(gi, step)
-        start = threading.Barrier(G + 1)
-
-        def drive(gi):
-            try:
-                torch.cuda.set_device(dev)
-                start.wait()
-                for step in range(5, 5 + T_host):
-                    one_step(gi, step)
-            except Exception as exc:      # surfaced by the main thread
-                errors.append(exc)
-
-        threads = [threading.Thread(target=drive, args=(gi,), daemon=True) for gi in range(G)]
-        for th in threads:
-            th.start()
         barrier()
         e0.record()
-        start.wait()
-        for th in threads:
-            th.join()
-        if errors:
-            raise errors[0]
+        for step in range(5, 5 + T_host):     # one host thread, round-robin over the halves (threads bought nothing)
+            for gi in range(G):
+                one_step(gi, step)
         pipe.drain()
         e1.record()
         barrier()
@@ -901,7 +883,7 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
                             "to pinned host memory every step, the host picks the next action from the returned mask "
                             "(hz_host_random_legal); no staging copies: the kernel reads the actions from and writes the rows "
                             "to the pinned buffers itself (hz_envs_host_step, one launch + one event record per half-step); two "
-                            "half-batches in flight on two streams, one host thread per half",
+                            "half-batches in flight on two streams, one host thread",
                     "bits_staged": {"value": e2e_staged, "what": "the same rows through device staging buffers: H2D copy, "
                                                                   "kernel, two D2H copies, replayed as one CUDA graph"},
                     "u8": {"value": e2e_u8, "d2h_bytes_per_step": d2h_u8},

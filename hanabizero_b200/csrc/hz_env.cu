@@ -890,50 +890,7 @@ int hz_envs_host_wait(hz_envs* e) {
   return HZ_OK;
 }
 
-namespace {
-struct SelTables {
-  uint8_t pop[256];
-  uint8_t sel[256][8];   // sel[v][k] = index of the k-th set bit of v
-  SelTables() {
-    for (int v = 0; v < 256; ++v) {
-      int n = 0;
-      for (int b = 0; b < 8; ++b) {
-        sel[v][b] = 0;
-        if ((v >> b) & 1) sel[v][n++] = (uint8_t)b;
-      }
-      pop[v] = (uint8_t)n;
-    }
-  }
-};
-const SelTables kSel;
-}  // namespace
-
-// Host-side helper for callers that drive the games from the CPU through the packed rows: a uniformly random legal
-// move per game, drawn from the legal-mask word of each row with a counter-based generator (seed, game, step).
-int hz_host_random_legal(const uint32_t* rows, int64_t ld_words, int legal_word, int num_games, int num_actions,
-                         uint64_t seed, uint32_t step, int32_t* out_actions) {
-  if (!rows || !out_actions || num_games < 0 || num_actions <= 0 || num_actions > 32 || legal_word < 0 || ld_words <= legal_word) {
-    set_error("hz_host_random_legal: bad argument");
-    return HZ_ERR_ARG;
-  }
-  const uint32_t amask = num_actions >= 32 ? 0xffffffffu : ((1u << num_actions) - 1u);
-  const unsigned long long step_key = (unsigned long long)step << 32;
-  for (int i = 0; i < num_games; ++i) {
-    uint32_t m = rows[(size_t)i * ld_words + legal_word] & amask;
-    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)i + 1ull) + step_key;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    // k-th set bit of m without data-dependent branches: per-byte counts, then a 256 x 8 select table
-    const uint32_t b0 = m & 255u, b1 = (m >> 8) & 255u, b2 = (m >> 16) & 255u, b3 = m >> 24;
-    const uint32_t c0 = kSel.pop[b0], c1 = c0 + kSel.pop[b1], c2 = c1 + kSel.pop[b2], c3 = c2 + kSel.pop[b3];
-    const uint32_t k = (uint32_t)(((x >> 32) * c3) >> 32);     // uniform in [0, popcount)
-    const uint32_t byte = (k >= c0) + (k >= c1) + (k >= c2);
-    const uint32_t base = byte == 0 ? 0u : (byte == 1 ? c0 : (byte == 2 ? c1 : c2));
-    const uint32_t bv = (m >> (8 * byte)) & 255u;
-    out_actions[i] = c3 ? (int32_t)(8 * byte + kSel.sel[bv][(k - base) & 7u]) : 0;
-  }
-  return HZ_OK;
-}
+// hz_host_random_legal (the host-side policy helper of this API) lives in hz_host.cpp: plain host C++.
 
 #ifdef HZ_TRACE
 int hz_debug_set_env_trace(long long* dev_buf) {   // debug build only (not in include/hzb200.h)
