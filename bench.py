@@ -747,18 +747,24 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
     rng = np.random.default_rng(11 + rank)
     acts_buf = torch.zeros(N, dtype=torch.int32, device=dev)
 
-    def device_pass(e, steps, lg, buf):
+    def device_pass(e, steps, lg, buf, fused):
+        """Random legal play on the device.  fused: the env kernel draws the next move itself
+        (hz_envs_set_random_policy; a step is ONE launch); else three torch kernels pick it from the legal mask."""
         for _ in range(steps):
-            buf.copy_(torch.argmax(lg * torch.rand_like(lg), dim=1))
+            if not fused:
+                buf.copy_(torch.argmax(lg * torch.rand_like(lg), dim=1))
             _, _, lg, _, _, _ = e.step_all(buf, auto_reset=True, want_local=False)
         return lg
 
-    def timed_graph(e, lg, buf, total_steps, per_graph=10):
-        lg = device_pass(e, 20, lg, buf)
+    def timed_graph(e, lg, buf, total_steps, per_graph=10, fused=True):
+        if fused:
+            e.set_random_policy(buf, seed=20 + rank)
+            _, _, lg = e.observe(want_local=False)          # draw 0: the moves of the current positions
+        lg = device_pass(e, 20, lg, buf, fused)
         torch.cuda.synchronize()
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
-            device_pass(e, per_graph, lg, buf)
+            device_pass(e, per_graph, lg, buf, fused)
         reps = max(total_steps // per_graph, 1)
         gr.replay()
         barrier()
@@ -767,8 +773,10 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
             gr.replay()
         e1.record()
         barrier()
+        e.set_random_policy(None)
         return world * e.num_games * reps * per_graph / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3), reps * per_graph
 
+    env_torch_policy, _ = timed_graph(env, legal, acts_buf, T, fused=False)
     env_value, steps_timed = timed_graph(env, legal, acts_buf, T)
     env.check()
 
@@ -869,11 +877,20 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
         by = N * b_env_step(env.global_dim, A, 4)
         env_roof = {"bound": "hbm", "kernel": "k_env<step,observe> (float32 observations)", "achieved": by / d2 / 1e9,
                     "peak": peak, "unit": "GB/s", "frac": by / d2 / 1e9 / peak, "traffic": None, "launch_us": d2 * 1e6,
-                    "algorithmic_bytes_per_game": b_env_step(env.global_dim, A, 4), "peak_source": peak_src}
+                    "algorithmic_bytes_per_game": b_env_step(env.global_dim, A, 4), "peak_source": peak_src,
+                    "games": N,
+                    "saturated": {"games": 65536, "achieved": sat["65536"] / world * b_env_step(env.global_dim, A, 4) / 1e9,
+                                  "frac": sat["65536"] / world * b_env_step(env.global_dim, A, 4) / 1e9 / peak,
+                                  "what": "the same kernel in the graph-replayed loop with 65536 games per GPU: at 4096 games "
+                                          "the launch lasts as long as its slowest game (a finished game re-deals ten cards "
+                                          "through dependent fp64 chains), with 16x the games the SMs stay busy"}}
     return {"metric": "hanabi_env_steps_per_sec", "value": env_value, "unit": "steps/s",
             "games_per_gpu": N, "steps_timed": steps_timed,
-            "includes": "on-device random legal action pick (3 torch kernels) + fused step/auto-reset/observe kernel, ten "
-                        "steps per CUDA graph",
+            "includes": "random legal play on the device: ONE launch per step (step + auto-reset + float32 global observation "
+                        "+ legal mask + the next random legal move, hz_envs_set_random_policy), ten steps per CUDA graph",
+            "with_torch_policy": {"value": env_torch_policy,
+                                  "what": "the same loop with the move picked by three torch kernels from the legal mask (what "
+                                          "round 1 timed)"},
             "saturated": {"what": "the same device-resident loop with more games per GPU than the search has trees",
                           "steps_per_s_by_games_per_gpu": sat},
             "e2e": {"value": e2e_bits, "unit": "steps/s", "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": d2h_bits,

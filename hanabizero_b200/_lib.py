@@ -76,6 +76,7 @@ SIGNATURES = {
     "hz_envs_step_observe_bits": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "hz_envs_host_step": (_i, [_vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "hz_envs_host_wait": (_i, [_vp]),
+    "hz_envs_set_random_policy": (_i, [_vp, _vp, _vp, C.c_uint64]),
     "hz_host_random_legal": (_i, [_vp, _i64, _i, _i, _i, C.c_uint64, C.c_uint32, _vp]),
     "hz_envs_check": (_i, [_vp, _vp, _vp]),
     "hz_envs_dump": (_i, [_vp, _vp, _vp]),

@@ -489,6 +489,12 @@ struct EnvArgs {
   uint32_t* out_bits;
   int64_t ld_bits;
   uint32_t* out_meta;   // optional [N][4]: {legal mask, reward, done, score} kept apart from the observation words
+  // fused random policy (hz_envs_set_random_policy): every observing launch also draws a uniformly random legal move
+  // of the position it observes — the k-th set bit of the legal mask, k from the splitmix64 finaliser over
+  // (seed, game, draws made so far), bit-identical to hz_host_random_legal(.., seed, step = draws made so far)
+  int32_t* policy_out;
+  uint32_t* policy_ctr;
+  unsigned long long policy_seed;
 };
 
 template <int C, int R, int H, int MI, int ML, bool RESET, bool STEP, bool OBSERVE>
@@ -589,8 +595,18 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
     if (og8) store_bits_u8(og8, words, 0, L::GLOBAL, lane);
     if (ol8) store_bits_u8(ol8, words, L::OWN, L::GLOBAL - L::OWN, lane);
     HZ_ESTAMP(7);
-    if (a.out_legal || a.out_legal8 || a.out_bits) {
+    if (a.out_legal || a.out_legal8 || a.out_bits || a.policy_out) {
       const unsigned legal_bits = legal_mask(st, g, lane);
+      if (a.policy_out && lane == 0) {
+        const uint32_t n = a.policy_ctr[gi];
+        unsigned long long x = a.policy_seed + 0x9E3779B97F4A7C15ull * ((unsigned long long)gi + 1ull) + ((unsigned long long)n << 32);
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        const uint32_t c = (uint32_t)__popc(legal_bits);
+        const uint32_t k = (uint32_t)(((x >> 32) * c) >> 32);          // uniform in [0, popcount)
+        a.policy_out[gi] = c ? (int32_t)(__fns(legal_bits, 0, (int)k + 1)) : 0;   // position of the k-th set bit
+        a.policy_ctr[gi] = n + 1u;
+      }
       if (lane < g.A) {
         const bool ok = (legal_bits >> lane) & 1u;
         if (a.out_legal) a.out_legal[(size_t)gi * g.A + lane] = ok ? 1.0f : 0.0f;
@@ -669,11 +685,16 @@ struct hz_envs {
   bool started = false;
   int dump_len = 0;
   cudaEvent_t host_done = nullptr;   // completion of the last hz_envs_host_step (created on first use)
+  int32_t* policy_out = nullptr;     // fused random policy (hz_envs_set_random_policy): caller-owned dev int32[N]
+  uint32_t* policy_ctr = nullptr;    // draws made per game (owned)
+  unsigned long long policy_seed = 0;
   EnvView view() const { return EnvView{state, mt, mti, err, N, g}; }
 };
 
 template <bool RESET, bool STEP, bool OBSERVE>
-static int launch_env(hz_envs* e, cudaStream_t s, const EnvArgs& a) {
+static int launch_env(hz_envs* e, cudaStream_t s, const EnvArgs& args) {
+  EnvArgs a = args;
+  if (OBSERVE) { a.policy_out = e->policy_out; a.policy_ctr = e->policy_ctr; a.policy_seed = e->policy_seed; }
   dim3 grid((e->N + kEnvWarps - 1) / kEnvWarps), block(kEnvWarps * HZ_WARP);
   if (e->preset == 0) {
     k_env<5, 5, 5, 8, 3, RESET, STEP, OBSERVE><<<grid, block, 0, s>>>(e->view(), a);
@@ -739,6 +760,7 @@ int hz_envs_destroy(hz_envs* e) {
   DeviceGuard dg(e->device);
   cudaFree(e->state); cudaFree(e->mt); cudaFree(e->mti); cudaFree(e->err);
   if (e->host_done) cudaEventDestroy(e->host_done);
+  cudaFree(e->policy_ctr);
   delete e;
   return HZ_OK;
 }
@@ -879,6 +901,19 @@ int hz_envs_host_step(hz_envs* e, void* stream, const int32_t* h_actions, int au
   if (int rc = hz_envs_step_observe_bits(e, stream, h_actions, nullptr, auto_reset, h_bits, ld_words, h_meta)) return rc;
   const cudaError_t ce = cudaEventRecord(e->host_done, (cudaStream_t)stream);
   if (ce != cudaSuccess) return fail_cuda(ce, "hz_envs_host_step: record");
+  return HZ_OK;
+}
+
+int hz_envs_set_random_policy(hz_envs* e, void* stream, int32_t* next_actions, uint64_t seed) {
+  if (!e) { set_error("hz_envs_set_random_policy: NULL handle"); return HZ_ERR_ARG; }
+  DeviceGuard dg(e->device);
+  if (next_actions && !e->policy_ctr) {
+    const cudaError_t ce = cudaMalloc(&e->policy_ctr, (size_t)e->N * sizeof(uint32_t));
+    if (ce != cudaSuccess) return fail_cuda(ce, "hz_envs_set_random_policy: counters");
+  }
+  if (next_actions) HZ_CUDA(cudaMemsetAsync(e->policy_ctr, 0, (size_t)e->N * sizeof(uint32_t), (cudaStream_t)stream));
+  e->policy_out = next_actions;
+  e->policy_seed = seed;
   return HZ_OK;
 }
 

@@ -165,6 +165,17 @@ class HanabiVecEnv:
                     reward=np.ascontiguousarray(m[:, 1]).view(np.int32), done=m[:, 2] != 0,
                     score=np.ascontiguousarray(m[:, 3]).view(np.int32))
 
+    def set_random_policy(self, next_actions, seed=0):
+        """Fused random policy (hz_envs_set_random_policy): from now on every observing launch also writes a uniformly
+        random legal move of each observed position into `next_actions` (int32 CUDA [N]; None switches it off) — hand
+        the same tensor to the next step_all / step_bits and a random-play step is one kernel launch.  Draw d of game
+        i equals random_legal_host(..., seed, step=d)[i]."""
+        if next_actions is not None and (next_actions.dtype != torch.int32 or next_actions.numel() != self.num_games
+                                         or not next_actions.is_cuda or not next_actions.is_contiguous()):
+            raise ValueError("next_actions must be a contiguous int32 CUDA tensor with one entry per game")
+        self._policy_buf = next_actions       # kept alive: the kernel writes into it
+        check(self._lib.hz_envs_set_random_policy(self._h, self._stream(), ptr(next_actions), int(seed) & (2 ** 64 - 1)))
+
     def random_legal_host(self, rows, out_actions, seed=0, step=0):
         """HOST: a uniformly random legal move per game into `out_actions` (CPU int32 tensor [n], e.g. pinned) from
         host rows holding the legal-mask word: packed rows [n, bits_words] (word W) or meta rows [n, 4] (word 0) —

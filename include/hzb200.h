@@ -235,6 +235,14 @@ int hz_envs_step_observe_bits(hz_envs* e, void* stream, const int32_t* actions, 
 int hz_envs_host_step(hz_envs* e, void* stream, const int32_t* h_actions, int auto_reset, uint32_t* h_bits,
                       int64_t ld_words, uint32_t* h_meta);
 int hz_envs_host_wait(hz_envs* e);
+/* Fused random policy for device-resident random play (rollouts, env throughput runs): after this call every
+ * observing launch of the handle (hz_envs_observe*, hz_envs_step_observe*, hz_envs_host_step) also writes, for every
+ * game it observes, a uniformly random legal move of the observed position into next_actions (dev int32[N], caller
+ * owned; 0 for a finished game) — pass the same buffer as `actions` of the next step and a whole random-play step is
+ * ONE launch.  Draw d of game i is the k-th legal move with k from the generator of hz_host_random_legal keyed
+ * (seed, i, step = d): the host twin reproduces any pick.  The per-game draw counters live on the device (CUDA-graph
+ * replays keep advancing them) and are reset to 0 by this call; next_actions == NULL switches the policy off. */
+int hz_envs_set_random_policy(hz_envs* e, void* stream, int32_t* next_actions, uint64_t seed);
 /* HOST helper for callers that drive the games from the CPU through the packed rows (no device work): a uniformly
  * random legal move per game from word `legal_word` (= W) of each host row, counter-based (seed, game, step). */
 int hz_host_random_legal(const uint32_t* rows, int64_t ld_words, int legal_word, int num_games, int num_actions,

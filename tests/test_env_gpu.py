@@ -279,3 +279,38 @@ def test_env_pipeline_matches_direct_stepping(fmt, zero_copy):
     for r, e in zip(refs, envs):
         assert torch.equal(r.dump(), e.dump())
         e.check()
+
+
+def test_fused_random_policy_equals_its_host_twin():
+    """hz_envs_set_random_policy: every observing launch also writes a random legal move per game; feeding the buffer
+    back makes a random-play step one launch.  Draw d of game i must equal hz_host_random_legal(seed, step=d) on the
+    legal mask of the position it was drawn for (CUDA-graph replays included: the draw counters live on the device)."""
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    n, seed = 130, 99
+    env = HanabiVecEnv(n, "Hanabi-Full", np.arange(n) + 5)
+    env.reset_all(observe=False)
+    buf = torch.zeros(n, dtype=torch.int32, device="cuda")
+    env.set_random_policy(buf, seed=seed)
+    rows = torch.zeros(n, env.bits_words - 4, dtype=torch.int32, device="cuda")
+    meta = torch.zeros(n, 4, dtype=torch.int32, device="cuda")
+    env.step_bits(None, out=rows, out_meta=meta)                 # observe: draw 0
+    host = torch.zeros(n, dtype=torch.int32)
+    graph = None
+    for d in range(40):
+        env.random_legal_host(meta.cpu(), host, seed=seed, step=d)
+        assert torch.equal(buf.cpu(), host), d
+        if d == 20:                                              # the second half replays a captured step
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                env.step_bits(buf, auto_reset=True, out=rows, out_meta=meta)
+        if graph is not None:
+            graph.replay()
+        else:
+            env.step_bits(buf, auto_reset=True, out=rows, out_meta=meta)   # plays the picks, writes the next ones
+    env.check()
+    env.set_random_policy(None)
+    before = buf.clone()
+    env.step_bits(buf, auto_reset=True, out=rows, out_meta=meta)
+    assert torch.equal(buf, before)                               # switched off: the buffer is no longer written
+    env.check()
