@@ -274,6 +274,20 @@ def reference_with_model(trees, A, S, game="Hanabi-Full", obs_dim=785):
         return f"unavailable: {type(e).__name__}: {e}"
 
 
+def config_obj(args, wl, world):
+    """The `config` object both arms print (same workload, same words): what is searched, not how."""
+    S, per = wl["sims"], wl["per_gpu"]
+    nodes_mb = per * (S + 1) * wl["A"] * 16 / 1e6
+    pool_mb = per * S * F_HIDDEN * (2 if args.amp == "torch_amp" else 4) / 1e6
+    return {"workload": f"{wl['name']}: {wl['total']} trees in total, {per} per GPU x {world} GPU(s) ({wl['scaling']} scaling), "
+                        f"{S - 1} simulations executed per search (core/mcts.py:25-26)",
+            "baseline_config": wl["config"], "trees_per_gpu": per, "trees_total": wl["total"], "actions": wl["A"],
+            "simulations": S, "stack": args.stack, "mdp": wl["mdp"],
+            "l2": f"per search the tree nodes ({nodes_mb:.0f} MB) + hidden pool ({pool_mb:.0f} MB) per GPU "
+                  f"{'exceed' if nodes_mb + pool_mb > 126 else 'fit'} the 126 MB L2; the GPU arm's roofline launches are timed "
+                  "with L2 flushed (256 MiB write) before each one"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -302,9 +316,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * trees * (S - 1) / val, "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{wl['name']}: {trees} trees in total ({wl['per_gpu']} per GPU x {args.gpus}), "
-                               f"{S - 1} simulations executed", "trees_total": trees, "actions": A, "simulations": S,
-                   "baseline_config": wl["config"]},
+        "config": config_obj(args, wl, max(args.gpus, 1)),
         "cpu_baseline": {"value": val, "unit": "simulations/s", "cores": out["cores"], "kind": out["kind"], "sample": sample},
         "e2e": {"value": val, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "env": {"metric": "hanabi_env_steps_per_sec", "value": env, "unit": "steps/s", "kind": out["env_kind"],
@@ -557,7 +569,7 @@ def run_ours(args):
     if world > 1 and wl["scaling"] == "strong" and not args.quick:
         wl_w = dict(wl, per_gpu=wl["total"], total=wl["total"] * world, scaling="weak")
         sbw = SearchBench(torch, args, wl_w, wl_w["per_gpu"], rank, world, dev, model)
-        kw = max(K // 2, 3)
+        kw = K if piped else max(K // 2, 3)      # whole waves of the pipeline
         ms_w, _, _ = time_searches(sbw, kw, 3, piped=piped)
         weak = {"value": wl_w["total"] * (S - 1) * kw / (ms_w * 1e-3), "unit": "simulations/s", "trees_per_gpu": wl_w["per_gpu"],
                 "trees_total": wl_w["total"], "ms_per_step": ms_w / kw, "steps": kw}
@@ -698,22 +710,18 @@ def run_ours(args):
                           "cffi), 1000 steps/core (2000 on 1 core) — what its callers pay per step")}
 
     if rank == 0:
-        nodes_mb = N * (S + 1) * A * 16 / 1e6
-        pool_mb = N * S * F * (2 if args.amp == "torch_amp" else 4) / 1e6
         line = {
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{wl['name']}: {wl['total']} trees in total, {N} per GPU x {world} GPU(s) ({wl['scaling']} "
-                                   f"scaling), {S - 1} simulations executed per search (core/mcts.py:25-26), {max(args.in_flight, 1)} independent "
-                                   f"search(es) in flight per GPU on their own streams, "
-                                   f"{'MuZeroNetFull' if wl['game'] == 'Hanabi-Full' else 'MuZeroNet'} random-init with re-drawn heads",
-                       "baseline_config": wl["config"], "trees_per_gpu": N, "trees_total": wl["total"], "actions": A,
-                       "simulations": S, "stack": args.stack, "mdp": wl["mdp"], "model_amp": args.amp,
-                       "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
-                       "searches_in_flight": max(args.in_flight, 1),
-                       "l2": f"per search the tree nodes ({nodes_mb:.0f} MB) + hidden pool ({pool_mb:.0f} MB) per GPU; the roofline "
-                             "launches are timed with L2 flushed (256 MiB write) before each one"},
+            "config": config_obj(args, wl, world),
+            "setup": {"network": f"{'MuZeroNetFull' if wl['game'] == 'Hanabi-Full' else 'MuZeroNet'} random-init with re-drawn heads, "
+                                 f"eval mode, BN folded, {'fp16' if args.amp == 'torch_amp' else 'fp32'} library GEMMs",
+                      "model_amp": args.amp, "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
+                      "searches_in_flight": max(args.in_flight, 1),
+                      "what": f"`value` and `e2e` keep {max(args.in_flight, 1)} independent searches of the workload's root batch in "
+                              "flight per GPU, each on its own stream (SearchPipeline: the reference's actors each own such a "
+                              "batch); `one_search_at_a_time` is the same K searches back to back"},
             "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "SearchPipeline.submit/wait (hanabizero_b200/mcts.py): pinned host inputs in, root statistics out, "
                            f"every search; {depth} searches in flight, each slot on its own compute stream, copies on two "
