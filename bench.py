@@ -374,12 +374,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": sorted(reasons)}
 
 
-def ncu_traffic_per_launch():
+def ncu_traffic_per_launch(trees):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the newest
-    committed `ncu --set full` capture of that kernel under profiles/; (None, None) if there is none."""
+    committed `ncu --set full` capture of that kernel at this tree count under profiles/
+    (r<NN>_ncu_full_k_search_step_<trees>.csv; captured with the caches left warm, as inside a search: the same capture
+    with ncu's default cache flush is the *_cold.csv next to it); (None, None) if there is none."""
     import csv
     import glob
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_k_search_step*.csv")), reverse=True):
+    paths = [p for p in glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_full_k_search_step_{trees}.csv"))]
+    for path in sorted(paths, reverse=True):
         try:
             rows = list(csv.reader(open(path)))
             hdr, units = rows[0], rows[1]
@@ -1009,7 +1012,7 @@ def tree_roofline(torch, args, wl, sb, model, lib):
     per_tree = b_sim(A, D, s_mean, F * eb / 4.0) + (2 * plan.n_support + A) * eb
     bytes_launch = N * per_tree
     achieved = bytes_launch / statistics.mean(durs) / 1e9
-    traffic, traffic_src = ncu_traffic_per_launch()
+    traffic, traffic_src = ncu_traffic_per_launch(N)
     return {"bound": "hbm", "kernel": "k_search_step<half,backprop,traverse> (hz_trees_search_step)",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
