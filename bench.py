@@ -70,7 +70,9 @@ def parse_args():
     p.add_argument("--env-steps", type=int, default=200, help="env steps per timed env pass")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-graph", action="store_true")
-    p.add_argument("--in-flight", type=int, default=4,
+    p.add_argument("--sm-target", type=int, default=None,
+                   help="SMs each in-flight search's library GEMMs are sized for (default: SearchPipeline's rule; 0 = whole device)")
+    p.add_argument("--in-flight", type=int, default=8,
                    help="independent searches kept in flight per GPU (SearchPipeline depth); 1 = one search at a time")
     p.add_argument("--quick", action="store_true", help="search + roofline only (skip env / self-play / extras)")
     return p.parse_args()
@@ -443,7 +445,8 @@ class SearchBench:
             from hanabizero_b200.mcts import SearchPipeline
             depth = max(1, self.args.in_flight)
             gather = AsyncStatsGather(self.n, self.A, self.dev, depth=depth) if self.world > 1 else None
-            self.pipe = SearchPipeline(self.mcts, self.model, self.n, self.A, depth=depth, device=self.dev, gather=gather)
+            self.pipe = SearchPipeline(self.mcts, self.model, self.n, self.A, depth=depth, device=self.dev, gather=gather,
+                                       gemm_sm_target=self.args.sm_target)
         self.pipe_ticket = self.pipe.submit(CONST["frac"], self.noise, self.zeros_r, self.root_logits, self.legal_i,
                                             self.root_hidden)
         return self.pipe_ticket
@@ -558,7 +561,10 @@ def run_ours(args):
     value_one = sims_total / (ms_one * 1e-3)
     if piped:
         ms_total, visits, gathered = time_searches(sb, K, W, piped=True)
-        assert torch.equal(visits, visits_one), "a search in the pipeline must equal the same search run alone"
+        # same inputs: identical trees when the pipeline runs the same library kernels; with GEMMs sized for a share of
+        # the SMs the network roundings differ in the last bits, so only the simulation count is checked then
+        assert sb.pipe.gemm_sm_target != 0 or torch.equal(visits, visits_one), "a search in the pipeline must equal the same search run alone"
+        assert int(visits.sum().item()) == N * (S - 1)
     else:
         ms_total, visits, gathered = time_searches(sb, K, W)
     value = sims_total / (ms_total * 1e-3)
@@ -615,7 +621,8 @@ def run_ours(args):
     e2e_serial = timed_e2e(e2e_step, warm=6)   # new Roots per search alternate between two cached handles: eager, capture, replay each
     # the same work through the double-buffered public API: the copies of neighbouring searches overlap the search
     depth = max(args.in_flight, 2)
-    pipe = sb.pipe if (sb.pipe is not None and world == 1) else SearchPipeline(mcts, model, N, A, depth=depth, device=dev)
+    pipe = sb.pipe if (sb.pipe is not None and world == 1) else SearchPipeline(mcts, model, N, A, depth=depth, device=dev,
+                                                                               gemm_sm_target=args.sm_target)
     depth = pipe.depth
     h_out = [(torch.empty(N, A, dtype=torch.int32).pin_memory(), torch.empty(N).pin_memory()) for _ in range(depth)]
     turn = [0]
@@ -627,7 +634,7 @@ def run_ours(args):
 
     e2e_value = timed_e2e(piped_step, pipe.drain, warm=3 * depth)   # each slot: one eager search, one capture, one replay
     assert int(h_out[0][0].sum().item()) == N * (S - 1) and torch.equal(h_out[0][0], h_out[1][0]), "pipelined search result"
-    assert torch.equal(h_out[0][0], h_visits), "pipelined and serial searches must agree"
+    assert pipe.gemm_sm_target != 0 or torch.equal(h_out[0][0], h_visits), "pipelined and serial searches must agree"
     h2d = sum(t.numel() * t.element_size() for t in (h_noise, h_logits, h_legal, h_hidden, h_reward))
     d2h = h_visits.numel() * 4 + h_values.numel() * 4
 
@@ -722,6 +729,7 @@ def run_ours(args):
                                  f"eval mode, BN folded, {'fp16' if args.amp == 'torch_amp' else 'fp32'} library GEMMs",
                       "model_amp": args.amp, "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
                       "searches_in_flight": max(args.in_flight, 1),
+                      "gemm_sm_target": (sb.pipe.gemm_sm_target if sb.pipe is not None else 0),
                       "what": f"`value` and `e2e` keep {max(args.in_flight, 1)} independent searches of the workload's root batch in "
                               "flight per GPU, each on its own stream (SearchPipeline: the reference's actors each own such a "
                               "batch); `one_search_at_a_time` is the same K searches back to back"},

@@ -45,6 +45,7 @@ SIGNATURES = {
     "hz_gemm_plan_destroy": (_i, [_vp]),
     "hz_gemm_plan_steps": (_i, [_vp]),
     "hz_gemm_plan_set_operand": (_i, [_vp, _i, _i, _vp]),
+    "hz_gemm_plan_set_sm_target": (_i, [_vp, _i]),
     "hz_gemm_launch_count": (_i64, []),
     "hz_gemm_plan_run": (_i, [_vp, _vp, _i, _i]),
     "hz_trees_set_progress": (_i, [_vp, _i]),

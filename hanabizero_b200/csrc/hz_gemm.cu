@@ -49,6 +49,7 @@ struct hz_gemm_plan {
   void* workspace = nullptr;
   size_t ws_bytes = 0;
   bool autotune = false;
+  int sm_target = 0;   // 0 = the whole device
   std::vector<LtStep> steps;
 };
 
@@ -61,39 +62,13 @@ struct hz_gemm_plan {
     }                                                                       \
   } while (0)
 
-static int build_step(hz_gemm_plan* p, LtStep& st) {
+// Heuristic choice of the library kernel for one step.  sm_target > 0 sets CUBLASLT_MATMUL_DESC_SM_COUNT_TARGET: the
+// heuristic then sizes the kernel for that many SMs (fewer, fatter CTAs) because concurrent streams are expected to use
+// the rest of the device — the setting for several searches in flight (SearchPipeline).
+static int select_algo(hz_gemm_plan* p, LtStep& st) {
   const hz_gemm_step& s = st.s;
-  const cudaDataType_t dt = p->elem_bytes == 2 ? CUDA_R_16F : CUDA_R_32F;
-  HZ_LT(cublasLtMatmulDescCreate(&st.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
-  const cublasOperation_t opT = CUBLAS_OP_T, opN = CUBLAS_OP_N;
-  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_TRANSA, &opT, sizeof(opT)));
-  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_TRANSB, &opN, sizeof(opN)));
-  cublasLtEpilogue_t epi = s.bias ? (s.relu ? CUBLASLT_EPILOGUE_RELU_BIAS : CUBLASLT_EPILOGUE_BIAS)
-                                  : (s.relu ? CUBLASLT_EPILOGUE_RELU : CUBLASLT_EPILOGUE_DEFAULT);
-  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &epi, sizeof(epi)));
-  if (s.bias) {
-    HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &s.bias, sizeof(s.bias)));
-    HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_BIAS_DATA_TYPE, &dt, sizeof(dt)));
-    if (s.batch > 1) {
-      int64_t bs = s.stride_bias;
-      HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_BIAS_BATCH_STRIDE, &bs, sizeof(bs)));
-    }
-  }
-  // column-major views: A_lt = W [k x n] ld=ldw, B_lt = A [k x m] ld=lda, C/D_lt [n x m]
-  HZ_LT(cublasLtMatrixLayoutCreate(&st.la, dt, s.k, s.n, s.ldw));
-  HZ_LT(cublasLtMatrixLayoutCreate(&st.lb, dt, s.k, s.m, s.lda));
-  HZ_LT(cublasLtMatrixLayoutCreate(&st.lc, dt, s.n, s.m, s.c ? s.ldc : s.ldd));
-  HZ_LT(cublasLtMatrixLayoutCreate(&st.ld, dt, s.n, s.m, s.ldd));
-  if (s.batch > 1) {
-    const int32_t bc = s.batch;
-    struct { cublasLtMatrixLayout_t l; int64_t stride; } lay[4] = {
-        {st.la, s.stride_w}, {st.lb, s.stride_a}, {st.lc, s.c ? s.stride_c : s.stride_d}, {st.ld, s.stride_d}};
-    for (auto& x : lay) {
-      HZ_LT(cublasLtMatrixLayoutSetAttribute(x.l, CUBLASLT_MATRIX_LAYOUT_BATCH_COUNT, &bc, sizeof(bc)));
-      HZ_LT(cublasLtMatrixLayoutSetAttribute(x.l, CUBLASLT_MATRIX_LAYOUT_STRIDED_BATCH_OFFSET, &x.stride, sizeof(x.stride)));
-    }
-  }
-  st.beta = s.c ? 1.0f : 0.0f;
+  int32_t target = p->sm_target > 0 ? p->sm_target : 0;
+  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_SM_COUNT_TARGET, &target, sizeof(target)));
   cublasLtMatmulPreference_t pref = nullptr;
   HZ_LT(cublasLtMatmulPreferenceCreate(&pref));
   HZ_LT(cublasLtMatmulPreferenceSetAttribute(pref, CUBLASLT_MATMUL_PREF_MAX_WORKSPACE_BYTES, &p->ws_bytes, sizeof(p->ws_bytes)));
@@ -150,6 +125,42 @@ static int build_step(hz_gemm_plan* p, LtStep& st) {
     cudaGetLastError();
   }
   return HZ_OK;
+}
+
+static int build_step(hz_gemm_plan* p, LtStep& st) {
+  const hz_gemm_step& s = st.s;
+  const cudaDataType_t dt = p->elem_bytes == 2 ? CUDA_R_16F : CUDA_R_32F;
+  HZ_LT(cublasLtMatmulDescCreate(&st.op, CUBLAS_COMPUTE_32F, CUDA_R_32F));
+  const cublasOperation_t opT = CUBLAS_OP_T, opN = CUBLAS_OP_N;
+  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_TRANSA, &opT, sizeof(opT)));
+  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_TRANSB, &opN, sizeof(opN)));
+  cublasLtEpilogue_t epi = s.bias ? (s.relu ? CUBLASLT_EPILOGUE_RELU_BIAS : CUBLASLT_EPILOGUE_BIAS)
+                                  : (s.relu ? CUBLASLT_EPILOGUE_RELU : CUBLASLT_EPILOGUE_DEFAULT);
+  HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_EPILOGUE, &epi, sizeof(epi)));
+  if (s.bias) {
+    HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_BIAS_POINTER, &s.bias, sizeof(s.bias)));
+    HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_BIAS_DATA_TYPE, &dt, sizeof(dt)));
+    if (s.batch > 1) {
+      int64_t bs = s.stride_bias;
+      HZ_LT(cublasLtMatmulDescSetAttribute(st.op, CUBLASLT_MATMUL_DESC_BIAS_BATCH_STRIDE, &bs, sizeof(bs)));
+    }
+  }
+  // column-major views: A_lt = W [k x n] ld=ldw, B_lt = A [k x m] ld=lda, C/D_lt [n x m]
+  HZ_LT(cublasLtMatrixLayoutCreate(&st.la, dt, s.k, s.n, s.ldw));
+  HZ_LT(cublasLtMatrixLayoutCreate(&st.lb, dt, s.k, s.m, s.lda));
+  HZ_LT(cublasLtMatrixLayoutCreate(&st.lc, dt, s.n, s.m, s.c ? s.ldc : s.ldd));
+  HZ_LT(cublasLtMatrixLayoutCreate(&st.ld, dt, s.n, s.m, s.ldd));
+  if (s.batch > 1) {
+    const int32_t bc = s.batch;
+    struct { cublasLtMatrixLayout_t l; int64_t stride; } lay[4] = {
+        {st.la, s.stride_w}, {st.lb, s.stride_a}, {st.lc, s.c ? s.stride_c : s.stride_d}, {st.ld, s.stride_d}};
+    for (auto& x : lay) {
+      HZ_LT(cublasLtMatrixLayoutSetAttribute(x.l, CUBLASLT_MATRIX_LAYOUT_BATCH_COUNT, &bc, sizeof(bc)));
+      HZ_LT(cublasLtMatrixLayoutSetAttribute(x.l, CUBLASLT_MATRIX_LAYOUT_STRIDED_BATCH_OFFSET, &x.stride, sizeof(x.stride)));
+    }
+  }
+  st.beta = s.c ? 1.0f : 0.0f;
+  return select_algo(p, st);
 }
 
 static void free_step(LtStep& st) {
@@ -226,6 +237,16 @@ int hz_gemm_plan_set_operand(hz_gemm_plan* p, int step, int which, void* ptr) {
   if (which == 0) s.a = ptr;
   else if (which == 1) s.c = ptr;
   else s.d = ptr;
+  return HZ_OK;
+}
+
+int hz_gemm_plan_set_sm_target(hz_gemm_plan* p, int sm_count) {
+  if (!p || sm_count < 0) { set_error("hz_gemm_plan_set_sm_target: bad argument"); return HZ_ERR_ARG; }
+  DeviceGuard dg(p->device);
+  p->sm_target = sm_count;
+  for (auto& st : p->steps) {
+    if (int rc = select_algo(p, st)) return rc;
+  }
   return HZ_OK;
 }
 

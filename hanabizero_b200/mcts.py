@@ -90,9 +90,10 @@ class MCTS(object):
         amp = getattr(self.config, "amp_type", "none") == "torch_amp"
         return model.recurrent_plan(torch.float16 if amp else torch.float32)
 
-    def _workspace(self, roots, model, hidden_state_roots):
+    def _workspace(self, roots, model, hidden_state_roots, gemm_sm_target=0):
         sims = int(self.config.num_simulations)
-        key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"), self.use_plan)
+        key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"), self.use_plan,
+               int(gemm_sm_target))
         ws = self._ws.get(key)
         if ws is not None and ws.model_ref() is not model:
             ws = None   # a different model object that happens to live at a recycled address
@@ -111,6 +112,7 @@ class MCTS(object):
             if len(self._ws) >= self.max_cached_workspaces:
                 self._ws.pop(next(iter(self._ws)))
             ws = self._ws[key] = _Workspace(roots, model, sims, feature, dtype)
+            ws.gemm_sm_target = int(gemm_sm_target)
         return ws
 
     def _simulate(self, roots, model, ws):
@@ -159,6 +161,8 @@ class MCTS(object):
             # run on different streams at the same time (SearchPipeline), and a captured graph keeps its buffers alive
             from .plan import BoundChain
             ws.chain = BoundChain(plan, roots.root_num)
+            if ws.gemm_sm_target:
+                ws.chain.set_sm_target(ws.gemm_sm_target)
         ch = ws.chain
         io = _lib.SearchIO()
         io.value_logits, io.ld_value = ptr(ch.value_logits), ch.value_logits.stride(0)
@@ -198,12 +202,14 @@ class MCTS(object):
                                         out.policy_logits, mm, results, sanitize_nan=True)
 
     # ---------------------------------------------------------------------------------------------
-    def run_multi(self, roots, model, hidden_state_roots, use_graph=True):
+    def run_multi(self, roots, model, hidden_state_roots, use_graph=True, gemm_sm_target=0):
         """core/mcts.py:11-57.  roots: cytree.Roots already prepared; hidden_state_roots: [N, F]
-        numpy array or tensor (any device).  Mutates `roots` in place and returns None."""
+        numpy array or tensor (any device).  Mutates `roots` in place and returns None.
+        gemm_sm_target > 0 sizes the network's library GEMMs for that many SMs instead of the whole device (for callers
+        that keep several searches in flight on different streams: SearchPipeline sets it)."""
         with torch.no_grad():
             model.eval()
-            ws = self._workspace(roots, model, hidden_state_roots)
+            ws = self._workspace(roots, model, hidden_state_roots, gemm_sm_target)
             if self._plan(model) is not None:
                 self._plan(model).refresh()   # re-fold weights in place if the module was updated
             ws.pool[0].copy_(cytree.as_device(hidden_state_roots, ws.pool.dtype, roots.device))
@@ -238,6 +244,18 @@ def _flat(x):
     return x.reshape(-1) if isinstance(x, torch.Tensor) else np.asarray(x).reshape(-1)
 
 
+def gemm_sm_target_for(num_roots, in_flight, device):
+    """SMs each search's library GEMMs should be sized for when `in_flight` independent searches of `num_roots` trees
+    share a GPU.  cuBLASLt sizes a GEMM to fill the whole device, so the GEMMs of different streams queue behind one
+    another; with small root batches it pays to size each for a share of the SMs so that they run side by side.
+    Measured on B200 (profiles/r02_sm_target.md): 3n/64 SMs up to half the device (24 at 512 trees, 48 at 1024, 74 at
+    2048); from ~3000 trees on the whole-device kernels are the best choice (returns 0)."""
+    if in_flight <= 1 or num_roots >= 3072:
+        return 0
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    return int(max(16, min(3 * num_roots // 64, sms // 2)))
+
+
 class SearchPipeline:
     """Searches kept in flight: `depth` slots, each with its own tree batch (and therefore its own captured search
     graph, network buffers and staging buffers) and its own compute stream.  Inputs are copied in on a copy stream and
@@ -257,11 +275,15 @@ class SearchPipeline:
     search's statistics over the ranks, off the compute streams; `gathered(t)` returns them.
     Weights must not change while searches are in flight: call drain() before updating the module."""
 
-    def __init__(self, mcts, model, num_roots, num_actions, depth=4, device=None, gather=None):
+    def __init__(self, mcts, model, num_roots, num_actions, depth=8, device=None, gather=None, gemm_sm_target=None):
         self.mcts, self.model = mcts, model
         self.n, self.a, self.depth = int(num_roots), int(num_actions), int(depth)
         self.device = next(model.parameters()).device if device is None else torch.device(device)
         dev, sims = self.device, int(mcts.config.num_simulations)
+        if gemm_sm_target is None:
+            gemm_sm_target = gemm_sm_target_for(self.n, self.depth, dev)
+        self.gemm_sm_target = int(gemm_sm_target)
+        mcts.max_cached_workspaces = max(mcts.max_cached_workspaces, self.depth + 4)   # one workspace (graph) per slot
         if gather is not None and gather.depth < self.depth:
             raise ValueError("gather.depth must be at least the pipeline depth")
         self.gather = gather
@@ -305,7 +327,7 @@ class SearchPipeline:
                 s["roots"].prepare(fraction, s["noise"], s["reward"], s["logits"], s["legal"])
             else:
                 s["roots"].prepare_no_noise(s["reward"], s["logits"], s["legal"])
-            self.mcts.run_multi(s["roots"], self.model, s["hidden"])
+            self.mcts.run_multi(s["roots"], self.model, s["hidden"], gemm_sm_target=self.gemm_sm_target)
             check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, compute.cuda_stream, ptr(s["visits"]),
                                                       ptr(s["values"])))
             s["ev_done"].record(compute)

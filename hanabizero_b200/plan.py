@@ -100,6 +100,10 @@ class BoundChain:
         check(plan.lib.hz_gemm_plan_create(C.byref(self._h), dev.index, self.x0.element_size(), arr, self.n_steps))
         self._state_ptr = self.state.data_ptr()   # where step 2 writes / step 3 reads the new hidden state
 
+    def set_sm_target(self, sm_count):
+        """Size the chain's library kernels for `sm_count` SMs (0 = the whole device): see hz_gemm_plan_set_sm_target."""
+        check(self.plan.lib.hz_gemm_plan_set_sm_target(self._h, int(sm_count)))
+
     def bind_state(self, state):
         """Make the dynamics network write its output (and the heads read it) at `state` ([n, F], plan dtype,
         contiguous) instead of the chain's own buffer: the search loop passes pool[x], so no copy is needed."""

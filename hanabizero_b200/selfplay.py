@@ -114,6 +114,7 @@ class SelfPlayEngine:
         self.noise_seed, self.game_offset, self.moves = int(noise_seed), int(game_offset), 0
         self.recorder = None
         self._roots = None
+        self.gemm_sm_target = 0      # SelfPlayPool sizes the search's GEMMs for a share of the SMs (mcts.gemm_sm_target_for)
         if record:
             from .trajectory import TrajectoryRecorder
             self.recorder = TrajectoryRecorder(num_games, self.obs_dim, self.env.num_actions, self.stack,
@@ -194,7 +195,7 @@ class SelfPlayEngine:
             roots.prepare(cfg.root_exploration_fraction, nz, zeros, logits.float(), legal_i)
         else:
             roots.prepare_no_noise(zeros, logits.float(), legal_i)
-        self.mcts.run_multi(roots, self.model, hidden)
+        self.mcts.run_multi(roots, self.model, hidden, gemm_sm_target=self.gemm_sm_target)
         self.moves += 1
         visits, values = roots.get_stats_tensors()
         actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
@@ -247,6 +248,9 @@ class SelfPlayPool:
             raise ValueError("SelfPlayPool needs at least one engine")
         dev = self.engines[0].dev
         self.streams = [torch.cuda.Stream(dev) for _ in self.engines]
+        from .mcts import gemm_sm_target_for
+        for eng in self.engines:
+            eng.gemm_sm_target = gemm_sm_target_for(eng.n, len(self.engines), dev)
         cur = torch.cuda.current_stream(dev)
         for s in self.streams:
             s.wait_stream(cur)       # engine construction ran on the caller's stream

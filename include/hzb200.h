@@ -372,6 +372,11 @@ int hz_gemm_plan_steps(const hz_gemm_plan* p);
  * dimension, 256-byte aligned.  Takes effect for the following hz_gemm_plan_run calls (and is what a CUDA graph
  * captures): the search loop makes the dynamics network write each new hidden state straight into pool[x]. */
 int hz_gemm_plan_set_operand(hz_gemm_plan* p, int step, int which, void* ptr);
+/* Size every step's library kernel for `sm_count` SMs instead of the whole device (CUBLASLT_MATMUL_DESC_SM_COUNT_TARGET;
+ * 0 = whole device, the default): the heuristic picks fewer, fatter CTAs, so the GEMMs of several plans running on
+ * different streams — independent searches in flight — share the GPU instead of queueing behind one another's
+ * grid-filling launches.  Re-selects the kernels at once; call before capturing the plan in a CUDA graph. */
+int hz_gemm_plan_set_sm_target(hz_gemm_plan* p, int sm_count);
 /* cuBLASLt launches issued through hz_gemm_plan_run in this process (library GEMMs, counted apart from
  * hz_launch_count, which counts this library's own kernels) */
 int64_t hz_gemm_launch_count(void);

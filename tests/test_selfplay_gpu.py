@@ -227,9 +227,11 @@ def test_selfplay_pool_equals_its_engines_stepped_alone():
     cfg = SearchConfig(num_simulations=S, amp_type="torch_amp")
     make = lambda e: SelfPlayEngine(N, "Hanabi-Full", model, cfg, seeds=np.arange(N) + 1000 * e, noise_seed=5,
                                     game_offset=e * N, device=dev)
+    from hanabizero_b200.mcts import gemm_sm_target_for
     alone = []
     for e in range(E):
         eng = make(e)
+        eng.gemm_sm_target = gemm_sm_target_for(N, E, dev)     # the pool's choice of library kernels => same roundings
         eng.reset()
         alone.append([{k: v.clone() for k, v in eng.step(deterministic=True).items()} for _ in range(moves)])
     torch.cuda.synchronize()
