@@ -497,6 +497,11 @@ def run_ours(args):
     wl = resolve_workload(args, world)
     N, A, S, F = wl["per_gpu"], wl["A"], wl["sims"], F_HIDDEN
     K, W = args.steps, max(args.warmup, 3)
+    # searches in flight: at most --in-flight, lowered so that the K timed searches split into equally full waves (a ragged
+    # last wave would run with fewer searches in flight than the figure claims)
+    if args.in_flight > 1:
+        waves = -(-K // args.in_flight)
+        args.in_flight = max(1, -(-K // waves))
     torch.manual_seed(0)
     net = MuZeroNetFull if wl["game"] == "Hanabi-Full" else MuZeroNet
     model = net(wl["obs_dim"] * args.stack, A).randomize_heads(seed=0).to(dev).eval()

@@ -1,0 +1,14 @@
+#!/bin/bash
+O=gpurun_out/r2y; mkdir -p $O
+for n in 512 1024 2048; do
+  timeout 300 python bench.py --quick --no-cpu-baseline --steps 20 --warmup 5 --trees-total $n > $O/b_$n.json 2> $O/b_$n.err; echo "$n rc=$?"
+done
+python - <<'P'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2y/b_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], 'value %.1fM'%(d['value']/1e6), 'one-at-a-time %.1fM'%(d['one_search_at_a_time']['value']/1e6), 'e2e %.1fM'%(d['e2e']['value']/1e6), d['setup']['searches_in_flight'], d['setup']['gemm_sm_target'])
+    except Exception as e:
+        print(f, 'ERR', e); print(open(f.replace('.json','.err')).read()[-800:])
+P
