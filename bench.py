@@ -529,6 +529,7 @@ def run_ours(args):
             for _ in range(max(warm, 3 * args.in_flight)):    # each slot: one eager search, one capture, one replay
                 bench.pipelined_step()
             bench.finish_pipeline()
+            bench.pipe.host_seconds, bench.pipe.submitted = 0.0, 0     # host time per submit: timed searches only
             barrier()
             e0.record()
             for _ in range(steps):
@@ -735,6 +736,7 @@ def run_ours(args):
                       "model_amp": args.amp, "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
                       "searches_in_flight": max(args.in_flight, 1),
                       "gemm_sm_target": (sb.pipe.gemm_sm_target if sb.pipe is not None else 0),
+                      "host_us_per_submit": (1e6 * sb.pipe.host_seconds / max(sb.pipe.submitted, 1) if sb.pipe is not None else None),
                       "what": f"`value` and `e2e` keep {max(args.in_flight, 1)} independent searches of the workload's root batch in "
                               "flight per GPU, each on its own stream (SearchPipeline: the reference's actors each own such a "
                               "batch); `one_search_at_a_time` is the same K searches back to back"},

@@ -86,13 +86,18 @@ def _device_index(device):
 def as_device(x, dtype, device, shape=None):
     """list / list of rows / numpy / torch (any device) -> contiguous CUDA tensor of `dtype`."""
     if isinstance(x, torch.Tensor):
-        t = x.detach().to(device=device, dtype=dtype, non_blocking=True)
+        if x.dtype == dtype and x.device == device and x.is_contiguous() and not x.requires_grad:
+            t = x       # already what the kernels take: no torch call at all
+        else:
+            t = x.detach().to(device=device, dtype=dtype, non_blocking=True)
     else:
         np_dtype = {torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64,
                     torch.uint8: np.uint8}.get(dtype, np.float32)
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np_dtype)).to(device=device, dtype=dtype)
     t = t.contiguous()
     if shape is not None:
+        if t.shape == tuple(shape):
+            return t
         if t.numel() != int(np.prod(shape)):
             raise ValueError(f"expected {tuple(shape)} values, got tensor of shape {tuple(t.shape)}")
         t = t.view(*shape)

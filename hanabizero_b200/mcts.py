@@ -18,6 +18,7 @@ device-resident path.  A model with only the reference's `recurrent_inference` (
 NetworkOutput) still works through the same kernels, paying that model's own host hops.
 """
 import contextlib
+import time
 import weakref
 
 import numpy as np
@@ -208,7 +209,8 @@ class MCTS(object):
         gemm_sm_target > 0 sizes the network's library GEMMs for that many SMs instead of the whole device (for callers
         that keep several searches in flight on different streams: SearchPipeline sets it)."""
         with torch.no_grad():
-            model.eval()
+            if getattr(model, "training", True):
+                model.eval()          # walks every submodule: only when something is still in training mode
             ws = self._workspace(roots, model, hidden_state_roots, gemm_sm_target)
             if self._plan(model) is not None:
                 self._plan(model).refresh()   # re-fold weights in place if the module was updated
@@ -270,8 +272,9 @@ class SearchPipeline:
         pipe.wait(t)          # out_visits / out_values now hold the result of that search
 
     Inputs are what Roots.prepare + MCTS.run_multi take (core/selfplay_worker.py:276-283): pinned host tensors
-    (pageable memory works but serialises the copies) or device tensors; outputs likewise.  `noises=None` selects
-    prepare_no_noise.  `gather` (dist.AsyncStatsGather with depth >= this depth) additionally all-gathers every
+    (pageable memory works but serialises the copies) or device tensors; outputs likewise.  Device tensors that already
+    have the staging buffers' type (float32 / int32 legal mask, contiguous, on this device) are read in place — keep
+    them unchanged until wait(ticket).  `noises=None` selects prepare_no_noise.  `gather` (dist.AsyncStatsGather with depth >= this depth) additionally all-gathers every
     search's statistics over the ranks, off the compute streams; `gathered(t)` returns them.
     Weights must not change while searches are in flight: call drain() before updating the module."""
 
@@ -298,6 +301,7 @@ class SearchPipeline:
                 values=torch.empty(self.n, device=dev), ticket=None,
                 ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False))
         self._next = 0
+        self.host_seconds, self.submitted = 0.0, 0
 
     def submit(self, fraction, noises, rewards, logits, legal, hidden_roots, out_visits=None, out_values=None):
         i = self._next
@@ -306,28 +310,37 @@ class SearchPipeline:
         if s["busy"]:
             s["ev_out"].synchronize()          # the slot's previous search has been read out
         s["busy"] = True
+        t_host = time.perf_counter()
         hidden_roots = torch.as_tensor(hidden_roots)
         if s["hidden"] is None or s["hidden"].shape != hidden_roots.shape or s["hidden"].dtype != hidden_roots.dtype:
             s["hidden"] = torch.empty(hidden_roots.shape, dtype=hidden_roots.dtype, device=self.device)
         caller = torch.cuda.current_stream(self.device)
-        self.copy_in.wait_stream(caller)       # device-resident inputs: whatever produced them on the caller's stream
-        with torch.cuda.stream(self.copy_in):
-            # the slot's staging buffers were last read by its previous search, which ev_out (waited above) follows
-            if noises is not None:
-                s["noise"].copy_(torch.as_tensor(noises), non_blocking=True)
-            s["reward"].copy_(torch.as_tensor(rewards), non_blocking=True)
-            s["logits"].copy_(torch.as_tensor(logits), non_blocking=True)
-            s["legal"].copy_(torch.as_tensor(legal), non_blocking=True)
-            s["hidden"].copy_(hidden_roots, non_blocking=True)
-            s["ev_in"].record(self.copy_in)
         compute = s["stream"]
-        compute.wait_event(s["ev_in"])
+        inputs = dict(noise=noises, reward=rewards, logits=logits, legal=legal, hidden=hidden_roots)
+        if all(v is None or self._usable_in_place(v, s[k]) for k, v in inputs.items()):
+            # device-resident inputs of the staging buffers' own type: read in place, no copies (the caller keeps them
+            # unchanged until wait(ticket)); the slot's stream only has to follow whatever produced them
+            compute.wait_stream(caller)
+            src = inputs
+        else:
+            self.copy_in.wait_stream(caller)
+            with torch.cuda.stream(self.copy_in):
+                # the slot's staging buffers were last read by its previous search, which ev_out (waited above) follows
+                if noises is not None:
+                    s["noise"].copy_(torch.as_tensor(noises), non_blocking=True)
+                s["reward"].copy_(torch.as_tensor(rewards), non_blocking=True)
+                s["logits"].copy_(torch.as_tensor(logits), non_blocking=True)
+                s["legal"].copy_(torch.as_tensor(legal), non_blocking=True)
+                s["hidden"].copy_(hidden_roots, non_blocking=True)
+                s["ev_in"].record(self.copy_in)
+            compute.wait_event(s["ev_in"])
+            src = s
         with torch.cuda.stream(compute):
             if noises is not None:
-                s["roots"].prepare(fraction, s["noise"], s["reward"], s["logits"], s["legal"])
+                s["roots"].prepare(fraction, src["noise"], src["reward"], src["logits"], src["legal"])
             else:
-                s["roots"].prepare_no_noise(s["reward"], s["logits"], s["legal"])
-            self.mcts.run_multi(s["roots"], self.model, s["hidden"], gemm_sm_target=self.gemm_sm_target)
+                s["roots"].prepare_no_noise(src["reward"], src["logits"], src["legal"])
+            self.mcts.run_multi(s["roots"], self.model, src["hidden"], gemm_sm_target=self.gemm_sm_target)
             check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, compute.cuda_stream, ptr(s["visits"]),
                                                       ptr(s["values"])))
             s["ev_done"].record(compute)
@@ -340,7 +353,13 @@ class SearchPipeline:
             if out_values is not None:
                 out_values.copy_(s["values"], non_blocking=True)
             s["ev_out"].record(self.copy_out)
+        self.host_seconds += time.perf_counter() - t_host   # host time spent enqueueing (not waiting for the GPU)
+        self.submitted += 1
         return i
+
+    def _usable_in_place(self, x, like):
+        return (isinstance(x, torch.Tensor) and x.device == like.device and x.dtype == like.dtype and x.shape == like.shape
+                and x.is_contiguous())
 
     def wait(self, ticket):
         self.slots[ticket]["ev_out"].synchronize()
