@@ -72,6 +72,8 @@ def parse_args():
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--sm-target", type=int, default=None,
                    help="SMs each in-flight search's library GEMMs are sized for (default: SearchPipeline's rule; 0 = whole device)")
+    p.add_argument("--stage-limit", type=int, default=None,
+                   help="hz_search_io.stage_limit of the in-flight searches (default: SearchPipeline's, 4; 0 = stage all that fits)")
     p.add_argument("--in-flight", type=int, default=8,
                    help="independent searches kept in flight per GPU (SearchPipeline depth); 1 = one search at a time")
     p.add_argument("--quick", action="store_true", help="search + roofline only (skip env / self-play / extras)")
@@ -446,7 +448,7 @@ class SearchBench:
             depth = max(1, self.args.in_flight)
             gather = AsyncStatsGather(self.n, self.A, self.dev, depth=depth) if self.world > 1 else None
             self.pipe = SearchPipeline(self.mcts, self.model, self.n, self.A, depth=depth, device=self.dev, gather=gather,
-                                       gemm_sm_target=self.args.sm_target)
+                                       gemm_sm_target=self.args.sm_target, stage_limit=self.args.stage_limit)
         self.pipe_ticket = self.pipe.submit(CONST["frac"], self.noise, self.zeros_r, self.root_logits, self.legal_i,
                                             self.root_hidden)
         return self.pipe_ticket
@@ -628,7 +630,8 @@ def run_ours(args):
     # the same work through the double-buffered public API: the copies of neighbouring searches overlap the search
     depth = max(args.in_flight, 2)
     pipe = sb.pipe if (sb.pipe is not None and world == 1) else SearchPipeline(mcts, model, N, A, depth=depth, device=dev,
-                                                                               gemm_sm_target=args.sm_target)
+                                                                               gemm_sm_target=args.sm_target,
+                                                                               stage_limit=args.stage_limit)
     depth = pipe.depth
     h_out = [(torch.empty(N, A, dtype=torch.int32).pin_memory(), torch.empty(N).pin_memory()) for _ in range(depth)]
     turn = [0]
@@ -736,6 +739,7 @@ def run_ours(args):
                       "model_amp": args.amp, "cuda_graph": not args.no_graph, "sharding": f"roots x{world}",
                       "searches_in_flight": max(args.in_flight, 1),
                       "gemm_sm_target": (sb.pipe.gemm_sm_target if sb.pipe is not None else 0),
+                      "tree_stage_limit": (sb.pipe.stage_limit if sb.pipe is not None else 0),
                       "host_us_per_submit": (1e6 * sb.pipe.host_seconds / max(sb.pipe.submitted, 1) if sb.pipe is not None else None),
                       "what": f"`value` and `e2e` keep {max(args.in_flight, 1)} independent searches of the workload's root batch in "
                               "flight per GPU, each on its own stream (SearchPipeline: the reference's actors each own such a "

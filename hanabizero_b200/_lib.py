@@ -93,7 +93,7 @@ class SearchIO(C.Structure):
                 ("sanitize_nan", C.c_int32), ("pool", _vp), ("state_cols", C.c_int32), ("out_batch", _vp),
                 ("ld_batch", _i64), ("onehot_cols", C.c_int32), ("out_ix", _vp), ("out_action", _vp),
                 ("minmax", _vp), ("value_delta_max", _f), ("discount", _f), ("pb_c_base", C.c_int32),
-                ("pb_c_init", _f), ("programmatic_launch", C.c_int32)]
+                ("pb_c_init", _f), ("programmatic_launch", C.c_int32), ("stage_limit", C.c_int32)]
 
 
 class TrajView(C.Structure):

@@ -91,10 +91,10 @@ class MCTS(object):
         amp = getattr(self.config, "amp_type", "none") == "torch_amp"
         return model.recurrent_plan(torch.float16 if amp else torch.float32)
 
-    def _workspace(self, roots, model, hidden_state_roots, gemm_sm_target=0):
+    def _workspace(self, roots, model, hidden_state_roots, gemm_sm_target=0, stage_limit=0):
         sims = int(self.config.num_simulations)
         key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"), self.use_plan,
-               int(gemm_sm_target))
+               int(gemm_sm_target), int(stage_limit))
         ws = self._ws.get(key)
         if ws is not None and ws.model_ref() is not model:
             ws = None   # a different model object that happens to live at a recycled address
@@ -113,7 +113,7 @@ class MCTS(object):
             if len(self._ws) >= self.max_cached_workspaces:
                 self._ws.pop(next(iter(self._ws)))
             ws = self._ws[key] = _Workspace(roots, model, sims, feature, dtype)
-            ws.gemm_sm_target = int(gemm_sm_target)
+            ws.gemm_sm_target, ws.stage_limit = int(gemm_sm_target), int(stage_limit)
         return ws
 
     def _simulate(self, roots, model, ws):
@@ -177,6 +177,7 @@ class MCTS(object):
         io.out_ix, io.out_action = ptr(ws.ix), ptr(ws.la)
         io.minmax, io.value_delta_max = ptr(mm.tensor(roots.device)), float(cfg.value_delta_max)
         io.discount, io.pb_c_base, io.pb_c_init = float(cfg.discount), int(cfg.pb_c_base), float(cfg.pb_c_init)
+        io.stage_limit = ws.stage_limit
         ref = _lib.C.byref(io)
         check(lib.hz_trees_search_step(h, st, 0, 1, ref))
         for x in range(1, sims):
@@ -203,15 +204,18 @@ class MCTS(object):
                                         out.policy_logits, mm, results, sanitize_nan=True)
 
     # ---------------------------------------------------------------------------------------------
-    def run_multi(self, roots, model, hidden_state_roots, use_graph=True, gemm_sm_target=0):
+    def run_multi(self, roots, model, hidden_state_roots, use_graph=True, gemm_sm_target=0, stage_limit=0):
         """core/mcts.py:11-57.  roots: cytree.Roots already prepared; hidden_state_roots: [N, F]
         numpy array or tensor (any device).  Mutates `roots` in place and returns None.
         gemm_sm_target > 0 sizes the network's library GEMMs for that many SMs instead of the whole device (for callers
-        that keep several searches in flight on different streams: SearchPipeline sets it)."""
+        that keep several searches in flight on different streams: SearchPipeline sets it); stage_limit > 0 likewise
+        shrinks the tree step's shared-memory staging so that it shares SMs with other searches' GEMMs
+        (hz_search_io.stage_limit).  Neither changes any result of the tree step; the SM target changes network
+        roundings in the last bits."""
         with torch.no_grad():
             if getattr(model, "training", True):
                 model.eval()          # walks every submodule: only when something is still in training mode
-            ws = self._workspace(roots, model, hidden_state_roots, gemm_sm_target)
+            ws = self._workspace(roots, model, hidden_state_roots, gemm_sm_target, stage_limit)
             if self._plan(model) is not None:
                 self._plan(model).refresh()   # re-fold weights in place if the module was updated
             ws.pool[0].copy_(cytree.as_device(hidden_state_roots, ws.pool.dtype, roots.device))
@@ -246,6 +250,9 @@ def _flat(x):
     return x.reshape(-1) if isinstance(x, torch.Tensor) else np.asarray(x).reshape(-1)
 
 
+STAGE_LIMIT_IN_FLIGHT = 4   # hz_search_io.stage_limit used when several searches share the GPU (profiles/r02_sm_target.md)
+
+
 def gemm_sm_target_for(num_roots, in_flight, device):
     """SMs each search's library GEMMs should be sized for when `in_flight` independent searches of `num_roots` trees
     share a GPU.  cuBLASLt sizes a GEMM to fill the whole device, so the GEMMs of different streams queue behind one
@@ -278,7 +285,8 @@ class SearchPipeline:
     search's statistics over the ranks, off the compute streams; `gathered(t)` returns them.
     Weights must not change while searches are in flight: call drain() before updating the module."""
 
-    def __init__(self, mcts, model, num_roots, num_actions, depth=8, device=None, gather=None, gemm_sm_target=None):
+    def __init__(self, mcts, model, num_roots, num_actions, depth=8, device=None, gather=None, gemm_sm_target=None,
+                 stage_limit=None):
         self.mcts, self.model = mcts, model
         self.n, self.a, self.depth = int(num_roots), int(num_actions), int(depth)
         self.device = next(model.parameters()).device if device is None else torch.device(device)
@@ -286,6 +294,8 @@ class SearchPipeline:
         if gemm_sm_target is None:
             gemm_sm_target = gemm_sm_target_for(self.n, self.depth, dev)
         self.gemm_sm_target = int(gemm_sm_target)
+        # searches in flight: a small staging region lets the tree step share SMs with the other slots' GEMM CTAs
+        self.stage_limit = (STAGE_LIMIT_IN_FLIGHT if self.depth > 1 else 0) if stage_limit is None else int(stage_limit)
         mcts.max_cached_workspaces = max(mcts.max_cached_workspaces, self.depth + 4)   # one workspace (graph) per slot
         if gather is not None and gather.depth < self.depth:
             raise ValueError("gather.depth must be at least the pipeline depth")
@@ -340,7 +350,8 @@ class SearchPipeline:
                 s["roots"].prepare(fraction, src["noise"], src["reward"], src["logits"], src["legal"])
             else:
                 s["roots"].prepare_no_noise(src["reward"], src["logits"], src["legal"])
-            self.mcts.run_multi(s["roots"], self.model, src["hidden"], gemm_sm_target=self.gemm_sm_target)
+            self.mcts.run_multi(s["roots"], self.model, src["hidden"], gemm_sm_target=self.gemm_sm_target,
+                                stage_limit=self.stage_limit)
             check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, compute.cuda_stream, ptr(s["visits"]),
                                                       ptr(s["values"])))
             s["ev_done"].record(compute)

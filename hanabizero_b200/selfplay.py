@@ -115,6 +115,7 @@ class SelfPlayEngine:
         self.recorder = None
         self._roots = None
         self.gemm_sm_target = 0      # SelfPlayPool sizes the search's GEMMs for a share of the SMs (mcts.gemm_sm_target_for)
+        self.stage_limit = 0         # ... and shrinks the tree step's staging (hz_search_io.stage_limit)
         if record:
             from .trajectory import TrajectoryRecorder
             self.recorder = TrajectoryRecorder(num_games, self.obs_dim, self.env.num_actions, self.stack,
@@ -195,7 +196,7 @@ class SelfPlayEngine:
             roots.prepare(cfg.root_exploration_fraction, nz, zeros, logits.float(), legal_i)
         else:
             roots.prepare_no_noise(zeros, logits.float(), legal_i)
-        self.mcts.run_multi(roots, self.model, hidden, gemm_sm_target=self.gemm_sm_target)
+        self.mcts.run_multi(roots, self.model, hidden, gemm_sm_target=self.gemm_sm_target, stage_limit=self.stage_limit)
         self.moves += 1
         visits, values = roots.get_stats_tensors()
         actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
@@ -248,9 +249,10 @@ class SelfPlayPool:
             raise ValueError("SelfPlayPool needs at least one engine")
         dev = self.engines[0].dev
         self.streams = [torch.cuda.Stream(dev) for _ in self.engines]
-        from .mcts import gemm_sm_target_for
+        from .mcts import STAGE_LIMIT_IN_FLIGHT, gemm_sm_target_for
         for eng in self.engines:
             eng.gemm_sm_target = gemm_sm_target_for(eng.n, len(self.engines), dev)
+            eng.stage_limit = STAGE_LIMIT_IN_FLIGHT if len(self.engines) > 1 else 0
         cur = torch.cuda.current_stream(dev)
         for s in self.streams:
             s.wait_stream(cur)       # engine construction ran on the caller's stream

@@ -128,6 +128,11 @@ typedef struct hz_search_io {
    * kernel of the stream drains and synchronises on it before reading the network outputs.  The caller guarantees
    * that the preceding kernel is not the previous tree step (there is at least one network kernel in between). */
   int32_t programmatic_launch;
+  /* > 0: stage at most this many expanded nodes' records in shared memory (and none of q).  0 = as much of the tree as
+   * fits, the fastest choice for a search that runs alone.  With several searches in flight on different streams a
+   * small limit (4) is better: the launch then needs ~6 KB of shared memory per CTA and shares SMs with the library
+   * GEMM CTAs of the other searches instead of waiting for SMs without one. */
+  int32_t stage_limit;
 } hz_search_io;
 int hz_trees_search_step(hz_trees* t, void* stream, int x, int do_traverse, const hz_search_io* io);
 

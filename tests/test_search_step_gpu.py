@@ -140,7 +140,7 @@ def test_search_step_deep_path_fallback():
     assert int(r["plen"].max()) > 40           # the path outgrew one warp: general routine taken
 
 
-def _search_step_vs_oracle(N, A, S, width, dtype, seed, tie=None, tree_offset=0, check_every=1, n_oracle=None):
+def _search_step_vs_oracle(N, A, S, width, dtype, seed, tie=None, tree_offset=0, check_every=1, n_oracle=None, stage_limit=0):
     """The production launch (hz_trees_search_step, hidden state written straight into pool[x] as the search loop
     does) in lock-step with the CPU oracle: the oracle is fed hz_support_decode's values/rewards (the same
     arithmetic sequence as the fused decode) and the policy logits as float32.  Compares (ix, action) per
@@ -187,6 +187,7 @@ def _search_step_vs_oracle(N, A, S, width, dtype, seed, tie=None, tree_offset=0,
     io.out_ix, io.out_action = ix.data_ptr(), la.data_ptr()
     io.minmax, io.value_delta_max = mmt.data_ptr(), CONST["delta"]
     io.discount, io.pb_c_base, io.pb_c_init = CONST["discount"], CONST["pb_c_base"], CONST["pb_c_init"]
+    io.stage_limit = stage_limit
     ref = ctypes.byref(io)
 
     def compare(x):
@@ -236,6 +237,13 @@ def _search_step_vs_oracle(N, A, S, width, dtype, seed, tie=None, tree_offset=0,
 ])
 def test_search_step_lockstep_vs_oracle(N, A, S, width, dtype, seed):
     _search_step_vs_oracle(N, A, S, width, dtype, seed, check_every=1 if N < 1000 else 8)
+
+
+@pytest.mark.parametrize("N,S,limit", [(200, 50, 4), (130, 50, 1), (2048, 200, 4)])
+def test_search_step_with_a_staging_limit_vs_oracle(N, S, limit):
+    """hz_search_io.stage_limit (the setting for several searches in flight: few nodes staged in shared memory, q read
+    from global memory) must not change a single bit."""
+    _search_step_vs_oracle(N, 20, S, 201, torch.float16, 21 + limit, check_every=1 if N < 1000 else 8, stage_limit=limit)
 
 
 def test_search_step_random_tie_break_matches_oracle_and_shards():
