@@ -257,12 +257,12 @@ def gemm_sm_target_for(num_roots, in_flight, device):
     """SMs each search's library GEMMs should be sized for when `in_flight` independent searches of `num_roots` trees
     share a GPU.  cuBLASLt sizes a GEMM to fill the whole device, so the GEMMs of different streams queue behind one
     another; with small root batches it pays to size each for a share of the SMs so that they run side by side.
-    Measured on B200 (profiles/r02_sm_target.md): 3n/64 SMs up to half the device (24 at 512 trees, 48 at 1024, 74 at
-    2048); from ~3000 trees on the whole-device kernels are the best choice (returns 0)."""
+    Measured on B200 (profiles/r02_sm_target.md): 3n/64 SMs up to 56 (24 at 512 trees, 48 at 1024, 56 at 1536-2048);
+    from ~3000 trees on the whole-device kernels are the best choice (returns 0)."""
     if in_flight <= 1 or num_roots >= 3072:
         return 0
     sms = torch.cuda.get_device_properties(device).multi_processor_count
-    return int(max(16, min(3 * num_roots // 64, sms // 2)))
+    return int(max(16, min(3 * num_roots // 64, 56 * sms // 148)))
 
 
 class SearchPipeline:

@@ -1,0 +1,15 @@
+#!/bin/bash
+O=gpurun_out/r3k; mkdir -p $O
+for cfg in "512 8 16" "512 8 32" "512 8 40" "512 12 24" "512 12 32" "1024 8 32" "1024 8 64" "1024 12 48" "2048 8 0" "2048 8 96" "2048 8 56" "4096 8 112" "4096 12 0"; do
+  set -- $cfg
+  timeout 300 python bench.py --quick --no-cpu-baseline --steps $(( $2 * 3 )) --warmup 3 --trees-total $1 --in-flight $2 --sm-target $3 > $O/b_$1_d$2_t$3.json 2> $O/b_$1_d$2_t$3.err; echo "$cfg rc=$?"
+done
+python - <<'P'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r3k/b_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], 'value %.1fM'%(d['value']/1e6), 'one-at-a-time %.1fM'%(d['one_search_at_a_time']['value']/1e6), 'e2e %.1fM'%(d['e2e']['value']/1e6), d['setup']['searches_in_flight'])
+    except Exception as e:
+        print(f, 'ERR', e); print(open(f.replace('.json','.err')).read()[-800:])
+P
