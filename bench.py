@@ -662,6 +662,9 @@ def run_ours(args):
                              "nn.Module path (PyTorch autocast kernels + generic tree calls) on the same roots and noise; the "
                              "trees are bit-exact functions of the network outputs, the difference is network rounding"}
         del roots_m
+        # the two paths are the same function up to the rounding of the network (fp16 storage, BN folding, library kernels)
+        assert agreement["root_action_agreement"] >= 0.99 or wl["config"] != 4 or N < 4096, \
+            f"production path picks a different root action on {1 - agreement['root_action_agreement']:.1%} of the trees"
 
     env_obj, selfplay_obj = None, None
     if not args.quick:
