@@ -314,3 +314,26 @@ def test_fused_random_policy_equals_its_host_twin():
     env.step_bits(buf, auto_reset=True, out=rows, out_meta=meta)
     assert torch.equal(buf, before)                               # switched off: the buffer is no longer written
     env.check()
+
+
+def test_host_step_rejects_pageable_memory_and_observes_without_actions():
+    """hz_envs_host_step reads and writes the caller's HOST buffers from the kernel: pinned memory works (also with
+    h_actions = NULL: observe only), ordinary pageable memory must be refused with an error instead of faulting."""
+    from hanabizero_b200 import _lib
+    from hanabizero_b200.hanabi_env import HanabiVecEnv
+    lib = _lib.load()
+    n = 33
+    env = HanabiVecEnv(n, "Hanabi-Full", np.arange(n) + 3)
+    g0, _, l0 = env.reset_all()
+    w = env.bits_words - 4
+    bits = torch.zeros(n, w, dtype=torch.int32).pin_memory()
+    meta = torch.zeros(n, 4, dtype=torch.int32).pin_memory()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.hz_envs_host_step(env._h, st, None, 1, bits.data_ptr(), w, meta.data_ptr()))
+    _lib.check(lib.hz_envs_host_wait(env._h))
+    u = env.unpack_bits(bits, meta)
+    assert (u["global_obs"] == g0.cpu().numpy()).all() and (u["legal"] == l0.cpu().numpy()).all()
+    pageable = torch.zeros(n, w, dtype=torch.int32)
+    rc = lib.hz_envs_host_step(env._h, st, None, 1, pageable.data_ptr(), w, meta.data_ptr())
+    assert rc != 0 and b"page-locked" in lib.hz_last_error()
+    env.check()

@@ -119,3 +119,29 @@ def test_gather_hidden_standalone():
     _lib.check(lib.hz_gather_hidden(torch.cuda.current_stream().cuda_stream, pool.data_ptr(), ix.data_ptr(), iy.data_ptr(),
                                     out.data_ptr(), N, F * 4))
     assert torch.equal(out, pool[ix.long(), iy.long()])
+
+
+@pytest.mark.parametrize("n,target", [(512, 24), (96, 16), (2048, 56)])
+def test_gemm_sm_target_keeps_the_function(n, target):
+    """hz_gemm_plan_set_sm_target only changes WHICH library kernels run (sized for a share of the SMs, for searches in
+    flight): the chain's outputs stay the same function — equal to the default kernels' within fp16 rounding — and
+    setting the target back to 0 restores the default kernels' bits."""
+    from hanabizero_b200.model import MuZeroNetFull
+    from hanabizero_b200.plan import BoundChain
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    model = MuZeroNetFull(785 * 4, 20).randomize_heads().to(dev).eval()
+    plan = model.recurrent_plan(torch.float16)
+    ch = BoundChain(plan, n)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    ch.x0.copy_(torch.rand(ch.x0.shape, device=dev, generator=gen).half())
+    st = torch.cuda.current_stream().cuda_stream
+    ch.run(st)
+    base_out, base_state = ch.out.clone(), ch.state.clone()
+    ch.set_sm_target(target)
+    ch.run(st)
+    torch.testing.assert_close(ch.out.float(), base_out.float(), rtol=2e-2, atol=4e-3)
+    torch.testing.assert_close(ch.state.float(), base_state.float(), rtol=2e-2, atol=4e-3)
+    ch.set_sm_target(0)
+    ch.run(st)
+    assert torch.equal(ch.out, base_out) and torch.equal(ch.state, base_state)
