@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence: launch list of a short bench, ncu --set full of the repo's two kernels (each program has exited 0
-# without ncu first: scripts/r2_run24.sh ran the same commands), raw pages exported to CSV on the box.
+# without ncu first: the same commands had been run plain before), raw pages exported to CSV on the box.
 O=gpurun_out/r3c; mkdir -p $O
 timeout 300 python scripts/prof_tree.py > $O/plain_tree.log 2>&1; echo "plain tree rc=$?"
 timeout 300 python scripts/prof_env.py > $O/plain_env.log 2>&1; echo "plain env rc=$?"

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: r2_scale.sh N   — config 4 (4096 trees in total, strong scaling) full line at N GPUs, config 5 (16384 x 200) quick line
+# usage: scale.sh N   — config 4 (4096 trees in total, strong scaling) full line at N GPUs, config 5 (16384 x 200) quick line
 N=$1; O=gpurun_out/r2scale; mkdir -p $O
 run() { if [ "$N" = "1" ]; then python bench.py "$@"; else python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py "$@"; fi; }
 timeout 900 bash -c "$(declare -f run); N=$N; run --gpus $N --steps 20 --warmup 5 --no-cpu-baseline" > $O/config4_${N}gpu.json 2> $O/config4_${N}gpu.err; echo "config4 x$N rc=$?"
