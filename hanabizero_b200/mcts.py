@@ -281,9 +281,16 @@ class SearchPipeline:
     Inputs are what Roots.prepare + MCTS.run_multi take (core/selfplay_worker.py:276-283): pinned host tensors
     (pageable memory works but serialises the copies) or device tensors; outputs likewise.  Device tensors that already
     have the staging buffers' type (float32 / int32 legal mask, contiguous, on this device) are read in place — keep
-    them unchanged until wait(ticket).  `noises=None` selects prepare_no_noise.  `gather` (dist.AsyncStatsGather with depth >= this depth) additionally all-gathers every
-    search's statistics over the ranks, off the compute streams; `gathered(t)` returns them.
-    Weights must not change while searches are in flight: call drain() before updating the module."""
+    them unchanged until wait(ticket).  `noises=None` selects prepare_no_noise.  `gather` (dist.AsyncStatsGather with
+    depth >= this depth) additionally all-gathers every search's statistics over the ranks, off the compute streams;
+    `gathered(t)` returns them.  Weights must not change while searches are in flight: call drain() before updating
+    the module.
+
+    Two settings make the slots share the GPU instead of queueing (profiles/r02_sm_target.md): `gemm_sm_target`
+    (default gemm_sm_target_for(num_roots, depth)) sizes each search's library GEMMs for a share of the SMs, and
+    `stage_limit` (default 4) keeps the tree step's shared-memory footprint small enough to sit next to a GEMM CTA.
+    Results per search are those of MCTS.run_multi with the same two settings (the SM target changes the rounding of
+    the network outputs in the last bits, the staging limit changes nothing)."""
 
     def __init__(self, mcts, model, num_roots, num_actions, depth=8, device=None, gather=None, gemm_sm_target=None,
                  stage_limit=None):
