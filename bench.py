@@ -378,14 +378,15 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": sorted(reasons)}
 
 
-def ncu_traffic_per_launch(trees):
+def ncu_traffic_per_launch(trees, stage_limit=0):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the newest
     committed `ncu --set full` capture of that kernel at this tree count under profiles/
     (r<NN>_ncu_full_k_search_step_<trees>.csv; captured with the caches left warm, as inside a search: the same capture
     with ncu's default cache flush is the *_cold.csv next to it); (None, None) if there is none."""
     import csv
     import glob
-    paths = [p for p in glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_full_k_search_step_{trees}.csv"))]
+    suffix = f"_stage_limit{stage_limit}" if stage_limit else ""
+    paths = [p for p in glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_full_k_search_step_{trees}{suffix}.csv"))]
     for path in sorted(paths, reverse=True):
         try:
             rows = list(csv.reader(open(path)))
@@ -953,11 +954,16 @@ def measured_peak():
     return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
-def tree_roofline(torch, args, wl, sb, model, lib):
+def tree_roofline(torch, args, wl, sb, model, lib, stage_limit=None):
     """Roofline of the dominant kernel of this repository — the fused tree step (hz_trees_search_step: decode +
     expand + back-propagate + min/max + traverse + hand-off) — timed live: one launch per simulation on synthetic
     network outputs, alone on the stream, L2 flushed before every launch; and the same launches back to back inside
-    a CUDA graph (what the search loop sees)."""
+    a CUDA graph (what the search loop sees).  The launch is the one the timed searches run: with the staging limit of
+    the searches in flight (hz_search_io.stage_limit); the variant a search that runs alone uses (everything staged) is
+    reported beside it."""
+    own_limit = stage_limit is None
+    if own_limit:
+        stage_limit = sb.pipe.stage_limit if sb.pipe is not None else 0
     from hanabizero_b200 import _lib, cytree
     N, A, S, F, dev = sb.n, sb.A, sb.S, F_HIDDEN, sb.dev
     peak, peak_src = measured_peak()
@@ -981,6 +987,7 @@ def tree_roofline(torch, args, wl, sb, model, lib):
     io.out_ix, io.out_action = None, None
     io.minmax, io.value_delta_max = mm.tensor(dev).data_ptr(), CONST["delta"]
     io.discount, io.pb_c_base, io.pb_c_init = CONST["discount"], CONST["pb_c_base"], CONST["pb_c_init"]
+    io.stage_limit = int(stage_limit)
     st = torch.cuda.current_stream().cuda_stream
     ref = _lib.C.byref(io)
     _lib.check(lib.hz_trees_search_step(roots.handle, st, 0, 1, ref))
@@ -1034,8 +1041,15 @@ def tree_roofline(torch, args, wl, sb, model, lib):
     per_tree = b_sim(A, D, s_mean, F * eb / 4.0) + (2 * plan.n_support + A) * eb
     bytes_launch = N * per_tree
     achieved = bytes_launch / statistics.mean(durs) / 1e9
-    traffic, traffic_src = ncu_traffic_per_launch(N)
+    traffic, traffic_src = ncu_traffic_per_launch(N, stage_limit)
+    solo = None
+    if own_limit and stage_limit != 0:     # the variant of a search that runs alone: the whole tree staged
+        full = tree_roofline(torch, args, wl, sb, model, lib, stage_limit=0)
+        solo = {k: full[k] for k in ("achieved", "frac", "launch_us", "launch_us_in_graph_no_flush", "frac_in_graph_no_flush",
+                                     "traffic", "traffic_source")}
+        solo["what"] = "the same launch with stage_limit = 0 (a search that runs alone: as much of the tree as fits is staged)"
     return {"bound": "hbm", "kernel": "k_search_step<half,backprop,traverse> (hz_trees_search_step)",
+            "stage_limit": int(stage_limit), "stage_all": solo,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "launch_us": 1e6 * statistics.mean(durs), "launch_us_in_graph_no_flush": warm_us,

@@ -1,5 +1,5 @@
 """Profiling driver: the fused tree step alone (hz_trees_search_step on synthetic network outputs), one launch per
-simulation, for `ncu --kernel-name regex:k_search_step`.   N=512 S=50 python scripts/prof_tree.py"""
+simulation, for `ncu --kernel-name regex:k_search_step`.   N=512 S=50 STAGE_LIMIT=0 python scripts/prof_tree.py"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -27,6 +27,7 @@ io.pool, io.state_cols = pool.data_ptr(), F
 io.out_batch, io.ld_batch, io.onehot_cols = ch.x0.data_ptr(), ch.x0.stride(0), plan.OH
 io.minmax, io.value_delta_max = mm.tensor(dev).data_ptr(), 0.006
 io.discount, io.pb_c_base, io.pb_c_init = 0.999, 19652, 1.25
+io.stage_limit = int(os.environ.get("STAGE_LIMIT", "0"))     # 4 = the setting of searches in flight
 st = torch.cuda.current_stream().cuda_stream; ref = ctypes.byref(io)
 gen = torch.Generator(device=dev).manual_seed(1)
 outs = [torch.randn(ch.out.shape, device=dev, generator=gen).half() for _ in range(8)]
