@@ -72,6 +72,7 @@ class AsyncStatsGather:
         i = self._next
         self._next = (i + 1) % self.depth
         s = self.slots[i]
+        s["flat"] = False
         if self.stream is None:       # gloo / CPU tensors: nothing to overlap with
             s["packed"][:, :self.a] = visits
             s["packed"][:, self.a] = values.contiguous().view(torch.int32)
@@ -97,9 +98,41 @@ class AsyncStatsGather:
         s["used"] = True
         return i
 
+    def submit_flat(self, flat):
+        """The same collective without any packing: `flat` is this rank's statistics already laid out as one int32
+        buffer [n * A visit counts | n value bit patterns] (SearchPipeline lets hz_trees_root_stats write straight
+        into such a buffer), gathered as it is.  Read the result with result(ticket) as usual."""
+        i = self._next
+        self._next = (i + 1) % self.depth
+        s = self.slots[i]
+        s["flat"] = True
+        if self.stream is None:
+            if self.world > 1:
+                dist.all_gather_into_tensor(s["out"].view(-1), flat, group=self.group)
+            else:
+                s["out"].view(-1).copy_(flat)
+            return i
+        cur = torch.cuda.current_stream(self.device)
+        if s["used"]:
+            cur.wait_event(s["done"])
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            if self.world > 1:
+                dist.all_gather_into_tensor(s["out"].view(-1), flat, group=self.group)
+            else:
+                s["out"].view(-1).copy_(flat, non_blocking=True)
+            s["done"].record(self.stream)
+        s["used"] = True                         # `flat` is a persistent buffer of the caller: no record_stream needed
+        return i
+
     def result(self, ticket):
         """(visits int32 [world*n, A], values float32 [world*n]) of a ticket; the current stream waits for it."""
         s = self.slots[ticket]
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_event(s["done"])
+        if s.get("flat"):      # per rank: [n * A visits | n values]
+            blocks = s["out"].view(self.world, self.n * (self.a + 1))
+            visits = blocks[:, :self.n * self.a].reshape(self.world * self.n, self.a)
+            values = blocks[:, self.n * self.a:].reshape(self.world * self.n).view(torch.float32)
+            return visits, values
         return s["out"][:, :self.a], s["out"][:, self.a].view(torch.float32)

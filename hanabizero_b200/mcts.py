@@ -314,9 +314,14 @@ class SearchPipeline:
                 roots=cytree.Roots(self.n, self.a, sims, device=dev), stream=torch.cuda.Stream(dev),
                 noise=torch.empty(self.n, self.a, device=dev), reward=torch.empty(self.n, device=dev),
                 logits=torch.empty(self.n, self.a, device=dev), legal=torch.empty(self.n, self.a, dtype=torch.int32, device=dev),
-                hidden=None, visits=torch.empty(self.n, self.a, dtype=torch.int32, device=dev),
-                values=torch.empty(self.n, device=dev), ticket=None,
+                hidden=None, stats=None, visits=None, values=None, ticket=None,
                 ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(), busy=False))
+        for s in self.slots:
+            # one int32 buffer [n * A visit counts | n value bit patterns]: the statistics kernel writes both parts in
+            # place and the all-gather ships the buffer as it is (no packing kernels)
+            s["stats"] = torch.empty(self.n * (self.a + 1), dtype=torch.int32, device=dev)
+            s["visits"] = s["stats"][:self.n * self.a].view(self.n, self.a)
+            s["values"] = s["stats"][self.n * self.a:].view(torch.float32)
         self._next = 0
         self.host_seconds, self.submitted = 0.0, 0
 
@@ -363,7 +368,7 @@ class SearchPipeline:
                                                       ptr(s["values"])))
             s["ev_done"].record(compute)
             if self.gather is not None:
-                s["ticket"] = self.gather.submit(s["visits"], s["values"])
+                s["ticket"] = self.gather.submit_flat(s["stats"])
         self.copy_out.wait_event(s["ev_done"])
         with torch.cuda.stream(self.copy_out):
             if out_visits is not None:

@@ -38,6 +38,13 @@ def _worker(rank, world, port, total, A, ragged, out_q):
         v1, val1 = ag.result(t1)
         ok = ok and bool((v0.numpy() == visits_all).all() and (val0.numpy() == values_all).all()
                          and (v1.numpy() == visits_all + 1).all() and (val1.numpy() == values_all * 2).all())
+        # the packing-free variant SearchPipeline uses: one buffer [n * A visits | n value bits] per rank
+        n = hi - lo
+        flat = torch.cat((torch.from_numpy(visits_all[lo:hi]).reshape(-1),
+                          torch.from_numpy(values_all[lo:hi].view(np.int32).copy())))
+        t2 = ag.submit_flat(flat)
+        v2, val2 = ag.result(t2)
+        ok = ok and bool((v2.numpy() == visits_all).all() and (val2.numpy().view(np.uint32) == values_all.view(np.uint32)).all())
     out_q.put((rank, ok, tuple(v.shape)))
     dist.barrier()
     dist.destroy_process_group()
