@@ -338,6 +338,10 @@ class SearchPipeline:
             s["hidden"] = torch.empty(hidden_roots.shape, dtype=hidden_roots.dtype, device=self.device)
         caller = torch.cuda.current_stream(self.device)
         compute = s["stream"]
+        if self.gather is not None and s["ticket"] is not None and self.gather.stream is not None:
+            # the slot's statistics buffer is the send buffer of its previous all-gather: the new search may only
+            # overwrite it once that collective is done
+            compute.wait_event(self.gather.slots[s["ticket"]]["done"])
         inputs = dict(noise=noises, reward=rewards, logits=logits, legal=legal, hidden=hidden_roots)
         if all(v is None or self._usable_in_place(v, s[k]) for k, v in inputs.items()):
             # device-resident inputs of the staging buffers' own type: read in place, no copies (the caller keeps them
