@@ -378,6 +378,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": sorted(reasons)}
 
 
+def ncu_env_traffic_per_launch(games):
+    """The same for the env kernel (profiles/r<NN>_ncu_full_k_env_<games>.csv, caches left warm)."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_full_k_env_{games}.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if "k_env" in r[ik]]
+            if vals:
+                return sum(vals) / len(vals), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def ncu_traffic_per_launch(trees, stage_limit=0):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused search-step kernel, from the newest
     committed `ncu --set full` capture of that kernel at this tree count under profiles/
@@ -909,8 +927,13 @@ def bench_env(torch, dist, args, wl, env, sb, barrier, max_over_ranks, e0, e1, r
         torch.cuda.synchronize()
         d2 = statistics.mean(a.elapsed_time(b) for a, b in evs) * 1e-3
         by = N * b_env_step(env.global_dim, A, 4)
+        env_traffic, env_traffic_src = ncu_env_traffic_per_launch(N)
         env_roof = {"bound": "hbm", "kernel": "k_env<step,observe> (float32 observations)", "achieved": by / d2 / 1e9,
-                    "peak": peak, "unit": "GB/s", "frac": by / d2 / 1e9 / peak, "traffic": None, "launch_us": d2 * 1e6,
+                    "peak": peak, "unit": "GB/s", "frac": by / d2 / 1e9 / peak, "traffic": env_traffic,
+                    "traffic_source": env_traffic_src,
+                    "traffic_note": "DRAM bytes with the caches as the previous step left them: the 13 MB of observations a "
+                                    "launch writes stay in the 126 MB L2, so DRAM sees almost nothing",
+                    "launch_us": d2 * 1e6,
                     "algorithmic_bytes_per_game": b_env_step(env.global_dim, A, 4), "peak_source": peak_src,
                     "games": N,
                     "saturated": {"games": 65536, "achieved": sat["65536"] / world * b_env_step(env.global_dim, A, 4) / 1e9,
