@@ -23,8 +23,10 @@ namespace hz {
 // debug build only: per-game cycle stamps of the env kernel's phases (scripts/exp_env_trace.py)
 __device__ long long* g_env_trace = nullptr;
 #define HZ_ESTAMP(k) do { if (g_env_trace && lane == 0) g_env_trace[(size_t)gi * 16 + (k)] = clock64(); } while (0)
+#define HZ_DSTAMP(k) do { if (g_env_trace && lane == 0) { const long long _c = clock64(); g_env_trace[(size_t)dgi * 16 + 10 + (k)] += _c - dt0; dt0 = _c; } } while (0)
 #else
 #define HZ_ESTAMP(k) do { } while (0)
+#define HZ_DSTAMP(k) do { } while (0)
 #endif
 
 constexpr int kEnvWarps = 4;
@@ -132,7 +134,11 @@ __device__ __forceinline__ void advance(uint8_t* st, int H) {  // hanabi_state.c
 // launch: these chains are the tail of the kernel.)
 template <int NT>
 __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_t* mt, int& mti, MtWindow& win,
-                                            double* scratch, int lane) {
+                                            double* scratch, int lane, int dgi = 0) {
+#ifdef HZ_TRACE
+  long long dt0 = clock64();
+  if (g_env_trace && lane == 0) g_env_trace[(size_t)dgi * 16 + 9] += 16;
+#endif
   const int cnt = lane < NT ? st[O_DECKCNT + lane] : 0;
   const bool have = cnt > 0;
   const unsigned mask = __ballot_sync(HZ_FULL, have);
@@ -144,15 +150,19 @@ __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_
     const double wv = have ? __ddiv_rn((double)cnt, (double)st[O_DECK]) : 0.0;
     w[lane] = wv;
     __syncwarp();
+    HZ_DSTAMP(0);
     double sum = 0.0;  // std::accumulate ascending
 #pragma unroll
     for (int i = 0; i < NT; ++i) sum = __dadd_rn(sum, w[i]);
+    HZ_DSTAMP(1);
     qn[lane] = have ? __ddiv_rn(wv, sum) : 0.0;  // __normalize
     __syncwarp();
+    HZ_DSTAMP(2);
     double acc = 0.0;  // std::partial_sum ascending, this lane's prefix
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc = __dadd_rn(acc, i <= lane ? qn[i] : 0.0);
     // lanes without an outcome never match; _M_cp.back() = 1.0
+    HZ_DSTAMP(3);
     const double cp = !have ? 2.0 : (lane == 31 - __clz(mask) ? 1.0 : acc);
     const uint32_t u0 = mt_draw(mt, mti, win, lane);
     const uint32_t u1 = mt_draw(mt, mti, win, lane);
@@ -162,6 +172,7 @@ __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_
     const unsigned ge = __ballot_sync(HZ_FULL, have && cp >= p);           // std::lower_bound
     pick = __ffs(ge) - 1;
     __syncwarp();
+    HZ_DSTAMP(4);
   }
   if (lane == 0) {
     const int to = player_to_deal(st, g.H);
@@ -177,6 +188,7 @@ __device__ __forceinline__ void deal_random(uint8_t* st, const Rules& g, uint32_
     advance(st, g.H);
   }
   __syncwarp();
+  HZ_DSTAMP(5);
 }
 
 // LegalMoves (hanabi_state.cc:288-304, MoveIsLegal 166-219) for all move uids at once, as a bit mask (warp-uniform):
@@ -524,7 +536,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
 
   if (RESET && (a.reset_mask == nullptr || a.reset_mask[gi])) {  // rl_env.py:249-252
     new_state(st, g, lane);
-    while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
+    while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane, gi);
     dirty = true;
   }
   if (STEP && (a.active == nullptr || a.active[gi])) {  // rl_env.py:413-438
@@ -541,7 +553,7 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
       apply_move(st, g, action, lane);
       __syncwarp();
       HZ_ESTAMP(2);
-      while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
+      while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane, gi);
       HZ_ESTAMP(3);
       score = score_of(st, C);
       reward = score - last_score;
@@ -549,9 +561,9 @@ __global__ void __launch_bounds__(kEnvWarps* HZ_WARP, 8) k_env(EnvView ev, EnvAr
       dirty = true;
       if (done && a.auto_reset) {
         new_state(st, g, lane);
-        while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane);
+        while ((int8_t)st[O_CUR] == -1) deal_random<C * R>(st, g, mt, mti, win, scratch, lane, gi);
 #ifdef HZ_TRACE
-        if (g_env_trace && lane == 0) g_env_trace[(size_t)gi * 16 + 9] = 1;
+        if (g_env_trace && lane == 0) g_env_trace[(size_t)gi * 16 + 9] += 1;
 #endif
       }
       HZ_ESTAMP(4);

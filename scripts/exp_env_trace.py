@@ -32,7 +32,7 @@ for t in range(120):
     torch.cuda.synchronize()
     if t >= 100 and t % 5 == 0:
         tr = trace.cpu().numpy().astype(np.float64)
-        reset = tr[:, 9] > 0
+        reset = (tr[:, 9] % 16) > 0
         names = [(0, 1, "legality check"), (1, 2, "apply_move (lane 0)"), (2, 3, "deal after the move"), (3, 4, "score/terminal (+ re-deal)"),
                  (4, 5, "state write-back"), (5, 6, "observation bits"), (6, 7, "expand + store floats"), (7, 8, "legal mask")]
         tot = tr[:, 8] - tr[:, 0]
@@ -42,5 +42,12 @@ for t in range(120):
             dd = tr[:, b] - tr[:, a]
             print(f"    {nm:28s} mean {dd.mean():7.0f}  p50 {np.median(dd):7.0f}  max {dd.max():7.0f}"
                   + (f"   re-dealt mean {dd[reset].mean():7.0f}" if reset.any() else ""))
+        deals = tr[:, 9] // 16
+        has = deals > 0
+        if has.any():
+            names2 = ["w = cnt/deck + sync", "sum chain (25 dadd)", "qn = w/sum + sync", "prefix chain (25 dadd)", "draws + pick", "apply deal (lane 0)"]
+            print(f"    per deal ({int(deals.sum())} deals over the traced steps):")
+            for k, nm in enumerate(names2):
+                print(f"        {nm:26s} {tr[has, 10 + k].sum() / deals.sum():7.0f} cycles")
         trace.zero_()
 env.check()
