@@ -48,6 +48,13 @@ SIGNATURES = {
     "hz_gemm_plan_set_sm_target": (_i, [_vp, _i]),
     "hz_gemm_launch_count": (_i64, []),
     "hz_gemm_plan_run": (_i, [_vp, _vp, _i, _i]),
+    "hz_rowchain_create": (_i, [C.POINTER(_vp), _i, _vp, _i, _vp, _i64, _vp, _vp]),
+    "hz_rowchain_destroy": (_i, [_vp]),
+    "hz_rowchain_set_state": (_i, [_vp, _vp]),
+    "hz_rowchain_run": (_i, [_vp, _vp]),
+    "hz_rowchain_grid": (_i, [_vp]),
+    "hz_rowchain_set_trace": (_i, [_vp, _i]),
+    "hz_rowchain_read_trace": (_i, [_vp, _vp, _i64]),
     "hz_trees_set_progress": (_i, [_vp, _i]),
     "hz_trees_set_tie_break": (_i, [_vp, _i, C.c_uint64, _i]),
     "hz_trees_root_stats": (_i, [_vp, _vp, _vp, _vp]),
@@ -101,6 +108,14 @@ class TrajView(C.Structure):
     _fields_ = [("obs", _vp), ("legal", _vp), ("action", _vp), ("reward", _vp), ("visits", _vp), ("root_value", _vp),
                 ("len", _vp), ("bank", _vp), ("finished", _vp), ("overflow", _vp), ("num", C.c_int32),
                 ("obs_dim", C.c_int32), ("actions", C.c_int32), ("stack", C.c_int32), ("max_len", C.c_int32), ("banks", C.c_int32)]
+
+
+class RowChainWeights(C.Structure):
+    """struct hz_rowchain_weights (include/hzb200.h)."""
+    _fields_ = [("w1", _vp), ("ld_w1", _i64), ("w1a_t", _vp), ("b1", _vp), ("w2", _vp), ("b2", _vp), ("w3", _vp),
+                ("b3", _vp), ("wh1", _vp), ("bh1", _vp), ("wb2", _vp), ("bb2", _vp), ("wa2", _vp), ("ba2", _vp),
+                ("wb3", _vp), ("bb3", _vp), ("state_cols", C.c_int32), ("head_cols", C.c_int32),
+                ("onehot_cols", C.c_int32), ("logit_cols", C.c_int32)]
 
 
 class GemmStep(C.Structure):

@@ -91,10 +91,10 @@ class MCTS(object):
         amp = getattr(self.config, "amp_type", "none") == "torch_amp"
         return model.recurrent_plan(torch.float16 if amp else torch.float32)
 
-    def _workspace(self, roots, model, hidden_state_roots, gemm_sm_target=0, stage_limit=0):
+    def _workspace(self, roots, model, hidden_state_roots, gemm_sm_target=0, stage_limit=0, executor="library"):
         sims = int(self.config.num_simulations)
         key = (roots.handle.value, id(model), sims, getattr(self.config, "amp_type", "none"), self.use_plan,
-               int(gemm_sm_target), int(stage_limit))
+               int(gemm_sm_target), int(stage_limit), executor)
         ws = self._ws.get(key)
         if ws is not None and ws.model_ref() is not model:
             ws = None   # a different model object that happens to live at a recycled address
@@ -113,7 +113,7 @@ class MCTS(object):
             if len(self._ws) >= self.max_cached_workspaces:
                 self._ws.pop(next(iter(self._ws)))
             ws = self._ws[key] = _Workspace(roots, model, sims, feature, dtype)
-            ws.gemm_sm_target, ws.stage_limit = int(gemm_sm_target), int(stage_limit)
+            ws.gemm_sm_target, ws.stage_limit, ws.executor = int(gemm_sm_target), int(stage_limit), executor
         return ws
 
     def _simulate(self, roots, model, ws):
@@ -164,6 +164,8 @@ class MCTS(object):
             ws.chain = BoundChain(plan, roots.root_num)
             if ws.gemm_sm_target:
                 ws.chain.set_sm_target(ws.gemm_sm_target)
+            if ws.executor == "rows" and ws.chain.rows_supported():
+                ws.chain.set_executor("rows")
         ch = ws.chain
         io = _lib.SearchIO()
         io.value_logits, io.ld_value = ptr(ch.value_logits), ch.value_logits.stride(0)
@@ -204,18 +206,20 @@ class MCTS(object):
                                         out.policy_logits, mm, results, sanitize_nan=True)
 
     # ---------------------------------------------------------------------------------------------
-    def run_multi(self, roots, model, hidden_state_roots, use_graph=True, gemm_sm_target=0, stage_limit=0):
+    def run_multi(self, roots, model, hidden_state_roots, use_graph=True, gemm_sm_target=0, stage_limit=0,
+                  executor="library"):
         """core/mcts.py:11-57.  roots: cytree.Roots already prepared; hidden_state_roots: [N, F]
         numpy array or tensor (any device).  Mutates `roots` in place and returns None.
         gemm_sm_target > 0 sizes the network's library GEMMs for that many SMs instead of the whole device (for callers
         that keep several searches in flight on different streams: SearchPipeline sets it); stage_limit > 0 likewise
         shrinks the tree step's shared-memory staging so that it shares SMs with other searches' GEMMs
-        (hz_search_io.stage_limit).  Neither changes any result of the tree step; the SM target changes network
-        roundings in the last bits."""
+        (hz_search_io.stage_limit).  executor="rows" runs the network as one row-block resident launch per simulation
+        (BoundChain.set_executor; fp16 Hanabi-Full plan, otherwise ignored).  None of them changes any result of the
+        tree step; the SM target and the executor change network roundings in the last bits."""
         with torch.no_grad():
             if getattr(model, "training", True):
                 model.eval()          # walks every submodule: only when something is still in training mode
-            ws = self._workspace(roots, model, hidden_state_roots, gemm_sm_target, stage_limit)
+            ws = self._workspace(roots, model, hidden_state_roots, gemm_sm_target, stage_limit, executor)
             if self._plan(model) is not None:
                 self._plan(model).refresh()   # re-fold weights in place if the module was updated
             ws.pool[0].copy_(cytree.as_device(hidden_state_roots, ws.pool.dtype, roots.device))
@@ -293,8 +297,9 @@ class SearchPipeline:
     the network outputs in the last bits, the staging limit changes nothing)."""
 
     def __init__(self, mcts, model, num_roots, num_actions, depth=8, device=None, gather=None, gemm_sm_target=None,
-                 stage_limit=None):
+                 stage_limit=None, executor="library"):
         self.mcts, self.model = mcts, model
+        self.executor = executor   # "rows": the network as one row-block resident launch (BoundChain.set_executor)
         self.n, self.a, self.depth = int(num_roots), int(num_actions), int(depth)
         self.device = next(model.parameters()).device if device is None else torch.device(device)
         dev, sims = self.device, int(mcts.config.num_simulations)
@@ -367,7 +372,7 @@ class SearchPipeline:
             else:
                 s["roots"].prepare_no_noise(src["reward"], src["logits"], src["legal"])
             self.mcts.run_multi(s["roots"], self.model, src["hidden"], gemm_sm_target=self.gemm_sm_target,
-                                stage_limit=self.stage_limit)
+                                stage_limit=self.stage_limit, executor=self.executor)
             check(s["roots"]._lib.hz_trees_root_stats(s["roots"].handle, compute.cuda_stream, ptr(s["visits"]),
                                                       ptr(s["values"])))
             s["ev_done"].record(compute)

@@ -99,6 +99,36 @@ class BoundChain:
         self._h = C.c_void_p()
         check(plan.lib.hz_gemm_plan_create(C.byref(self._h), dev.index, self.x0.element_size(), arr, self.n_steps))
         self._state_ptr = self.state.data_ptr()   # where step 2 writes / step 3 reads the new hidden state
+        self._rows, self._use_rows = C.c_void_p(), False
+
+    def rows_supported(self):
+        """The row-block resident executor (hz_rowchain, include/hzb200.h) covers the fp16 Hanabi-Full plan."""
+        p = self.plan
+        return bool(p.full and p.dtype == torch.float16 and p.F == 512 and p.H == 256 and p.OH == 32 and p.P3 <= 256)
+
+    def set_executor(self, name):
+        """"library": seven cuBLASLt launches (lowest latency for one search on an idle GPU).  "rows": ONE launch in
+        which each CTA carries 128 rows through the whole chain (hz_rowchain): 1/4 of the SMs at 4096 rows, for
+        searches in flight.  Same function; roundings differ in the last fp16 bits."""
+        if name not in ("library", "rows"):
+            raise ValueError("executor must be 'library' or 'rows'")
+        if name == "rows":
+            if not self.rows_supported():
+                raise RuntimeError("the row-block executor needs the fp16 Hanabi-Full plan (F=512, H=256)")
+            if not self._rows:
+                p, w = self.plan, self.plan._w
+                ws = _lib.RowChainWeights()
+                ws.w1, ws.ld_w1, ws.w1a_t, ws.b1 = w["W1"].data_ptr(), w["W1"].stride(0), w["W1aT"].data_ptr(), w["b1"].data_ptr()
+                ws.w2, ws.b2, ws.w3, ws.b3 = w["W2"].data_ptr(), w["b2"].data_ptr(), w["W3"].data_ptr(), w["b3"].data_ptr()
+                ws.wh1, ws.bh1 = w["Wh1"].data_ptr(), w["bh1"].data_ptr()
+                ws.wb2, ws.bb2 = w["WB2"].data_ptr(), w["bB2"].data_ptr()
+                ws.wa2, ws.ba2 = w["Wa2"].data_ptr(), w["ba2"].data_ptr()
+                ws.wb3, ws.bb3 = w["WB3"].data_ptr(), w["bB3"].data_ptr()
+                ws.state_cols, ws.head_cols, ws.onehot_cols, ws.logit_cols = p.F, p.H, p.OH, p.P3
+                check(p.lib.hz_rowchain_create(C.byref(self._rows), p.device.index, C.byref(ws), self.n,
+                                               self.x0.data_ptr(), self.x0.stride(0), self._state_ptr,
+                                               self.out.data_ptr()))
+        self._use_rows = name == "rows"
 
     def set_sm_target(self, sm_count):
         """Size the chain's library kernels for `sm_count` SMs (0 = the whole device): see hz_gemm_plan_set_sm_target."""
@@ -113,6 +143,8 @@ class BoundChain:
                 raise ValueError("bind_state: shape/dtype/layout must match the chain's state buffer")
             check(self.plan.lib.hz_gemm_plan_set_operand(self._h, 2, 2, p))   # fc3: D
             check(self.plan.lib.hz_gemm_plan_set_operand(self._h, 3, 0, p))   # heads' first layer: A
+            if self._rows:
+                check(self.plan.lib.hz_rowchain_set_state(self._rows, p))
             self._state_ptr = p
 
     def __del__(self):
@@ -123,9 +155,19 @@ class BoundChain:
             except Exception:
                 pass
             self._h = None
+        r = getattr(self, "_rows", None)
+        if r:
+            try:
+                self.plan.lib.hz_rowchain_destroy(r)
+            except Exception:
+                pass
+            self._rows = C.c_void_p()
 
     def run(self, stream):
-        check(self.plan.lib.hz_gemm_plan_run(self._h, stream, 0, self.n_steps))
+        if self._use_rows:
+            check(self.plan.lib.hz_rowchain_run(self._rows, stream))
+        else:
+            check(self.plan.lib.hz_gemm_plan_run(self._h, stream, 0, self.n_steps))
 
     @property
     def value_logits(self):
@@ -198,6 +240,7 @@ class RecurrentPlan:
         w1c = w1.new_zeros(F, self.KP)
         w1c[:, :F + A] = w1
         self._set("W1", w1c)
+        self._set("W1aT", w1c[:, F:].t())          # [OH, F]: the action columns of fc1, one row per action (hz_rowchain)
         self._set("b1", b1)
         for i, (fc, bn) in ((2, (d.fc2, d.bn2)), (3, (d.fc3, d.bn3))):
             w, b = _fold(fc, bn)
