@@ -39,21 +39,24 @@ constexpr int kActBytes = kBM * kF * 2;            // 128 KB: 8 K-blocks
 constexpr int kWSlot = 256 * kBK * 2;              // 32 KB: a weight tile of up to 256 output columns x 64 k
 constexpr int kWSlots = 3;
 constexpr int kOffW = kActBytes, kOffAux = kOffW + kWSlots * kWSlot;
-constexpr int kRowSmem = kOffAux + 1024 + 1024;    // aux + alignment slack: 231 424 bytes (limit 232 448)
+constexpr int kAuxBytes = 128 + 1024;              // barriers + the phase's biases (2 jobs x 256 halfs)
+constexpr int kRowSmem = kOffAux + kAuxBytes + 1024;   // + alignment slack: 231 552 bytes (limit 232 448)
 constexpr int kEpiWarps = 16, kEpiThreads = kEpiWarps * 32, kRowThreads = 64 + kEpiThreads;
-constexpr int kMaxPhases = 10, kMaps = 7;
+constexpr int kMaxPhases = 10, kMaps = 10;          // 7 weight maps + x0, state, out
+constexpr int kMapX0 = 7, kMapState = 8, kMapOut = 9;
 constexpr unsigned kSpin = 1u << 26;               // a stuck wait traps instead of hanging the GPU
 
 struct RowJob {
   int32_t map, n0, batch, num_k, a_kb, n, half;   // weight tile source, A K-block offset, MMA N, TMEM half
   int32_t relu, dst_kb;                           // dst_kb >= 0: write fp16 into activation K-blocks dst_kb..
   int32_t res, res_off;                           // 0 none | 1 W1aT[action] + res_off | 2 x0 hidden + res_off | 3 activation K-block res_off
-  int32_t gout, gb;                               // 0 none | 1 copy the activation tile to `state` | 2 out[gb] directly
+  int32_t gout, gb;                               // 0 none | 1 TMA-store the tile to `state` | 2 TMA-store K-blocks dst_kb.. to out[gb]
   int32_t pad_;
   const __half* bias;
 };
 struct RowPhase {
   int32_t njobs, after;                           // after: 0 nothing | 1 reload s' | 2 load the next row block's s
+  int32_t a_wait, pad_;                           // the MMAs also wait for a TMA-loaded activation tile
   RowJob job[2];
 };
 struct alignas(64) RowParams {
@@ -95,6 +98,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all_but_last() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -166,22 +178,6 @@ __device__ __forceinline__ void stamp(const RowParams& P, int phase, int slot) {
 
 using namespace rc;
 
-// rows [rb * 128, +128) of a [rows][ld] fp16 matrix (first 512 columns) -> activation tile; rows past the end are zero
-template <bool kBypassL1>
-__device__ __forceinline__ void load_rows(uint32_t act, const __half* src, int64_t ld, int rb, int rows, int et) {
-#pragma unroll 4
-  for (int idx = et; idx < kBM * (kF / 8); idx += kEpiThreads) {
-    const int r = idx >> 6, ch = idx & 63;
-    const int row = rb * kBM + r;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < rows) {
-      const uint4* p = reinterpret_cast<const uint4*>(src + (size_t)row * ld + 8 * ch);
-      v = kBypassL1 ? __ldcg(p) : *p;
-    }
-    st_shared_v4(act + act_off(r, ch), v);
-  }
-}
-
 __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_constant__ RowParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024-byte alignment
@@ -190,7 +186,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
   auto w_empty = [&](int s) { return aux + 8u * (kWSlots + s); };
   auto acc_full = [&](int h) { return aux + 8u * (2 * kWSlots + h); };
   const uint32_t act_ready = aux + 8u * (2 * kWSlots + 2);
-  const uint32_t tmem_slot = act_ready + 8u;
+  const uint32_t a_full = act_ready + 8u;       // a TMA-loaded activation tile (s, or s' coming back) has landed
+  const uint32_t tmem_slot = a_full + 8u;
+  const uint32_t sbias = aux + 128u;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -198,6 +196,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
     mbar_init(acc_full(0), 1);
     mbar_init(acc_full(1), 1);
     mbar_init(act_ready, kEpiWarps);
+    mbar_init(a_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int m = 0; m < kMaps; ++m) tma_prefetch_desc(&P.maps[m]);
   }
@@ -237,13 +236,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one();
-    uint32_t slot = 0, f_par = 0, ar_par = 0;
+    uint32_t slot = 0, f_par = 0, ar_par = 0, af_par = 0;
     bool first_rb = true;
     for (int rb = blockIdx.x; rb < P.row_blocks; rb += gridDim.x) {
       for (int ph = 0; ph < P.n_phases; ++ph) {
         const RowPhase& F = P.phase[ph];
         mbar_wait(act_ready, ar_par);        // the activation tile is written and both accumulators are drained
         ar_par ^= 1u;
+        if (F.a_wait) {
+          mbar_wait(a_full, af_par);
+          af_par ^= 1u;
+        }
         tc_fence_after();
         if (leader && first_rb) stamp(P, ph, 0);
         for (int j = 0; j < F.njobs; ++j) {
@@ -280,8 +283,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
     const int rloc = q * 32 + lane;
     uint32_t a_par = 0;                        // bit h: parity of acc_full(h)'s next completion
     bool first_rb = true;
-    load_rows<false>(act, P.x0, P.ld_x0, blockIdx.x, P.rows, et);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // all traffic between the activation tile and global memory is bulk-asynchronous and issued by ONE thread (et 0):
+    // loads of s / s' complete on a_full, stores of s' and of the logits are bulk groups it waits for before the tile
+    // is reused
+    auto load_tile = [&](int map, int rb_) {
+      mbar_expect_tx(a_full, kActBytes);
+#pragma unroll
+      for (int kb = 0; kb < kF / kBK; ++kb) tma_load_3d(act + kb * kKB, &P.maps[map], a_full, kb * kBK, rb_ * kBM, 0);
+    };
+    if (et == 0) load_tile(kMapX0, blockIdx.x);
     __syncwarp();
     if (lane == 0) mbar_arrive(act_ready);
     for (int rb = blockIdx.x; rb < P.row_blocks; rb += gridDim.x) {
@@ -289,11 +299,21 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
       const bool live = row < P.rows;
       for (int ph = 0; ph < P.n_phases; ++ph) {
         const RowPhase& F = P.phase[ph];
-        // residual sources that live in global memory are resolved while the MMAs run
+        // ---- while the MMAs run: this phase's biases -> shared memory, residual rows resolved, first chunks requested
+        if (et == 0) tma_wait_read_all();   // bulk stores issued so far have read the tile: it may be overwritten again
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");    // ... and the previous phase's bias readers are done
+        {
+          const int j = et >> 8, col = et & 255;
+          if (j < F.njobs && col < F.job[j].n) {
+            const unsigned short bv = __half_as_ushort(F.job[j].bias[col]);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbias + 2u * et), "h"(bv) : "memory");
+          }
+        }
         const __half* crow[2] = {nullptr, nullptr};
+        uint4 ef0 = make_uint4(0, 0, 0, 0), ef1 = ef0;    // job 0's first residual chunk, requested before the wait
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (j >= F.njobs) break;
+          if (j >= F.njobs) continue;
           const RowJob& J = F.job[j];
           if (J.res == 1 && live) {
             const uint4* oh = reinterpret_cast<const uint4*>(P.x0 + (size_t)row * P.ld_x0 + kF);
@@ -312,7 +332,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
           } else if (J.res == 2 && live) {
             crow[j] = P.x0 + (size_t)row * P.ld_x0 + J.res_off;
           }
+          if (j == 0 && crow[0]) {
+            const int c0 = ((part * (J.n >> 4)) >> 2) * 16;
+            ef0 = __ldg(reinterpret_cast<const uint4*>(crow[0] + c0));
+            ef1 = __ldg(reinterpret_cast<const uint4*>(crow[0] + c0 + 8));
+          }
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");    // biases staged
         // every job of the phase must have finished reading the activation tile before any of it is overwritten
         for (int j = 0; j < F.njobs; ++j) {
           const int h = F.job[j].half;
@@ -321,100 +347,122 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
         }
         tc_fence_after();
         if (et == 0 && first_rb) stamp(P, ph, 2);
-        bool copy_state = false;
+        bool any_store = false;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (j >= F.njobs) break;
+          if (j >= F.njobs) continue;
           const RowJob& J = F.job[j];
           const int n16 = J.n >> 4;
           const int c_begin = ((part * n16) >> 2) * 16, c_end = (((part + 1) * n16) >> 2) * 16;
           const uint32_t t_addr = tmem_base + (uint32_t)J.half * 256u + ((uint32_t)(q * 32) << 16);
+          const uint32_t sb = sbias + (uint32_t)j * 512u;
           const __half* cr = crow[j];
-          copy_state |= J.gout == 1;
-          uint32_t r[16], rn[16];
-          if (c_begin < c_end) {
-            tc_ld16(t_addr + (uint32_t)c_begin, r);
-            tc_wait_ld();
-          }
-          for (int c = c_begin; c < c_end; c += 16) {
-            const bool more = c + 16 < c_end;
-            if (more) tc_ld16(t_addr + (uint32_t)(c + 16), rn);   // in flight while this chunk is processed
-            const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(J.bias + c));
-            const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(J.bias + c + 8));
-            uint4 e0 = make_uint4(0, 0, 0, 0), e1 = e0;
-            if (cr) {
-              e0 = __ldg(reinterpret_cast<const uint4*>(cr + c));
-              e1 = __ldg(reinterpret_cast<const uint4*>(cr + c + 8));
-            } else if (J.res == 3) {
-              const int ch = J.res_off * 8 + (c >> 3);
+          const int res = J.res, relu = J.relu, dst_kb = J.dst_kb, res_off = J.res_off;
+          any_store |= J.gout != 0;
+          // residual of columns [c, c + 16) of this thread's row (zero when the row has none)
+          auto fetch_res = [&](int c, uint4& e0, uint4& e1) {
+            if (res == 3) {
+              const int ch = res_off * 8 + (c >> 3);
               e0 = ld_shared_v4(act + act_off(rloc, ch));
               e1 = ld_shared_v4(act + act_off(rloc, ch + 1));
+            } else if (cr) {
+              e0 = __ldg(reinterpret_cast<const uint4*>(cr + c));
+              e1 = __ldg(reinterpret_cast<const uint4*>(cr + c + 8));
             }
+          };
+          auto emit = [&](const uint32_t (&r)[16], const uint4& e0, const uint4& e1, int c) {
+            const uint4 b0 = ld_shared_v4(sb + 2u * (uint32_t)c), b1 = ld_shared_v4(sb + 2u * (uint32_t)c + 16u);
             float v[16];
-            {
-              const __half2* h0 = reinterpret_cast<const __half2*>(&b0);
-              const __half2* h1 = reinterpret_cast<const __half2*>(&b1);
+            const __half2* h0 = reinterpret_cast<const __half2*>(&b0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&b1);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
+              v[2 * t] = __uint_as_float(r[2 * t]) + f0.x;
+              v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) + f0.y;
+              v[8 + 2 * t] = __uint_as_float(r[8 + 2 * t]) + f1.x;
+              v[8 + 2 * t + 1] = __uint_as_float(r[8 + 2 * t + 1]) + f1.y;
+            }
+            if (res != 0) {
               const __half2* g0 = reinterpret_cast<const __half2*>(&e0);
               const __half2* g1 = reinterpret_cast<const __half2*>(&e1);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
-                const float2 f0 = __half22float2(h0[t]), f1 = __half22float2(h1[t]);
                 const float2 x0 = __half22float2(g0[t]), x1 = __half22float2(g1[t]);
-                v[2 * t] = __uint_as_float(r[2 * t]) + f0.x + x0.x;
-                v[2 * t + 1] = __uint_as_float(r[2 * t + 1]) + f0.y + x0.y;
-                v[8 + 2 * t] = __uint_as_float(r[8 + 2 * t]) + f1.x + x1.x;
-                v[8 + 2 * t + 1] = __uint_as_float(r[8 + 2 * t + 1]) + f1.y + x1.y;
+                v[2 * t] += x0.x; v[2 * t + 1] += x0.y; v[8 + 2 * t] += x1.x; v[8 + 2 * t + 1] += x1.y;
               }
-            }
-            if (J.relu) {
-#pragma unroll
-              for (int t = 0; t < 16; ++t) v[t] = fmaxf(v[t], 0.0f);
             }
             uint4 o0, o1;
-            {
-              __half2* p0 = reinterpret_cast<__half2*>(&o0);
-              __half2* p1 = reinterpret_cast<__half2*>(&o1);
+            __half2* p0 = reinterpret_cast<__half2*>(&o0);
+            __half2* p1 = reinterpret_cast<__half2*>(&o1);
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                p0[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
-                p1[t] = __floats2half2_rn(v[8 + 2 * t], v[8 + 2 * t + 1]);
-              }
+            for (int t = 0; t < 4; ++t) {
+              p0[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+              p1[t] = __floats2half2_rn(v[8 + 2 * t], v[8 + 2 * t + 1]);
             }
-            if (J.dst_kb >= 0) {
-              const int ch = J.dst_kb * 8 + (c >> 3);
+            if (relu) {   // rounding is monotonic and keeps the sign: max(round(x), 0) == round(max(x, 0))
+              const __half2 z = __float2half2_rn(0.0f);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) { p0[t] = __hmax2(p0[t], z); p1[t] = __hmax2(p1[t], z); }
+            }
+            if (dst_kb >= 0) {
+              const int ch = dst_kb * 8 + (c >> 3);
               st_shared_v4(act + act_off(rloc, ch), o0);
               st_shared_v4(act + act_off(rloc, ch + 1), o1);
             }
-            if (J.gout == 2 && live) {
-              uint4* g = reinterpret_cast<uint4*>(P.out + ((size_t)J.gb * P.rows + row) * P.p3 + c);
-              g[0] = o0;
-              g[1] = o1;
+          };
+          uint32_t ra[16], rb2[16];
+          uint4 ea0 = ef0, ea1 = ef1, eb0 = make_uint4(0, 0, 0, 0), eb1 = eb0;
+          if (j == 1 || res == 3) {
+            ea0 = ea1 = make_uint4(0, 0, 0, 0);
+            fetch_res(c_begin, ea0, ea1);
+          }
+          tc_ld16(t_addr + (uint32_t)c_begin, ra);
+          for (int c = c_begin; c < c_end; c += 32) {
+            tc_wait_ld();
+            const bool more1 = c + 16 < c_end;
+            if (more1) {                         // the next chunk's accumulators and residual travel while this one is processed
+              tc_ld16(t_addr + (uint32_t)(c + 16), rb2);
+              if (res != 0) fetch_res(c + 16, eb0, eb1);
             }
-            if (more) {
+            emit(ra, ea0, ea1, c);
+            if (more1) {
               tc_wait_ld();
-#pragma unroll
-              for (int t = 0; t < 16; ++t) r[t] = rn[t];
+              if (c + 32 < c_end) {
+                tc_ld16(t_addr + (uint32_t)(c + 32), ra);
+                if (res != 0) fetch_res(c + 32, ea0, ea1);
+              }
+              emit(rb2, eb0, eb1, c + 16);
             }
           }
         }
-        if (copy_state) {
-          // s' is complete in the activation tile: copy it to the pool with row-contiguous 16-byte stores
+        if (any_store || F.after != 0) {
+          // the tile (s', or the staged logits) goes out as bulk tensor stores; what comes in next follows them
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          for (int idx = et; idx < kBM * (kF / 8); idx += kEpiThreads) {
-            const int rr = idx >> 6, ch = idx & 63;
-            if (rb * kBM + rr < P.rows) {
-              const uint4 o = ld_shared_v4(act + act_off(rr, ch));
-              *reinterpret_cast<uint4*>(P.state + (size_t)(rb * kBM + rr) * kF + 8 * ch) = o;
+          if (et == 0) {
+            for (int j = 0; j < F.njobs; ++j) {
+              const RowJob& J = F.job[j];
+              if (J.gout == 1 && j == 0) {
+                for (int kb = 0; kb < kF / kBK; ++kb) tma_store_3d(&P.maps[kMapState], act + kb * kKB, kb * kBK, rb * kBM, 0);
+              } else if (J.gout == 2) {
+                for (int i = 0; i * kBK < P.p3; ++i)
+                  tma_store_3d(&P.maps[kMapOut], act + (J.dst_kb + i) * kKB, i * kBK, rb * kBM, J.gb);
+              }
+            }
+            if (any_store) tma_commit();
+            if (F.after == 1) {
+              // the value/reward branch is done with the tile: s' comes back for the policy branch once its own store
+              // (an earlier group) is complete and the logits just issued have been read
+              tma_wait_all_but_last();
+              tma_wait_read_all();
+              asm volatile("fence.proxy.async;" ::: "memory");
+              load_tile(kMapState, rb);
+            } else if (F.after == 2 && rb + (int)gridDim.x < P.row_blocks) {
+              tma_wait_read_all();
+              load_tile(kMapX0, rb + gridDim.x);
             }
           }
-        }
-        if (F.after == 1) {
-          // the value/reward branch is done with the tile: bring s' back for the policy branch (this CTA wrote it)
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          load_rows<true>(act, P.state, kF, rb, P.rows, et);
-        } else if (F.after == 2 && rb + (int)gridDim.x < P.row_blocks) {
-          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-          load_rows<false>(act, P.x0, P.ld_x0, rb + gridDim.x, P.rows, et);
         }
         if (et == 0 && first_rb) stamp(P, ph, 3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -426,6 +474,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
     }
   }
 
+  if (threadIdx.x == 64) tma_wait_all();   // the bulk stores read this CTA's shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -505,7 +554,12 @@ int hz_rowchain_create(hz_rowchain** out, int device, const hz_rowchain_weights*
             make_w_map(&P.maps[3], w->wh1, kF, 3 * kH, 1, kF, 256) &&
             make_w_map(&P.maps[4], w->wb2, kH, kH, 3, kH, 256) &&
             make_w_map(&P.maps[5], w->wa2, kH, kH, 1, kH, 256) &&
-            make_w_map(&P.maps[6], w->wb3, kH, p3, 3, kH, p3);
+            make_w_map(&P.maps[6], w->wb3, kH, p3, 3, kH, p3) &&
+            // activations: boxes of 128 rows x 64 columns, the K-blocks of the tile (rows past the end read as zero
+            // and are not written)
+            make_w_map(&P.maps[kMapX0], x0, kF, rows, 1, ld_x0, kBM) &&
+            make_w_map(&P.maps[kMapState], state, kF, rows, 1, kF, kBM) &&
+            make_w_map(&P.maps[kMapOut], out_logits, p3, rows, 3, p3, kBM);
   if (!ok) { delete e; set_error("hz_rowchain_create: cuTensorMapEncodeTiled failed"); return HZ_ERR_CUDA; }
   const __half *b1 = (const __half*)w->b1, *b2 = (const __half*)w->b2, *b3 = (const __half*)w->b3,
                *bh1 = (const __half*)w->bh1, *bb2 = (const __half*)w->bb2, *ba2 = (const __half*)w->ba2,
@@ -519,27 +573,28 @@ int hz_rowchain_create(hz_rowchain** out, int device, const hz_rowchain_weights*
     return j;
   };
   int np = 0;
-  auto phase = [&](int after, RowJob j0, const RowJob* j1 = nullptr) {
+  auto phase = [&](int after, RowJob j0, const RowJob* j1 = nullptr, int a_wait = 0) {
     RowPhase& F = P.phase[np++];
-    F.after = after; F.njobs = j1 ? 2 : 1; F.job[0] = j0;
+    F.after = after; F.njobs = j1 ? 2 : 1; F.job[0] = j0; F.a_wait = a_wait;
     if (j1) F.job[1] = *j1;
   };
   RowJob t;
   // dynamics
-  t = job(0, 256, 0, 8, 0, 256, 1, b1 + 256, 1, 4, 1, 256);  phase(0, job(0, 0, 0, 8, 0, 256, 0, b1, 1, 0, 1, 0), &t);
+  t = job(0, 256, 0, 8, 0, 256, 1, b1 + 256, 1, 4, 1, 256);  phase(0, job(0, 0, 0, 8, 0, 256, 0, b1, 1, 0, 1, 0), &t, 1);
   t = job(1, 256, 0, 8, 0, 256, 1, b2 + 256, 1, 4);          phase(0, job(1, 0, 0, 8, 0, 256, 0, b2, 1, 0), &t);
   t = job(2, 256, 0, 8, 0, 256, 1, b3 + 256, 1, 4, 2, 256, 1);
   phase(0, job(2, 0, 0, 8, 0, 256, 0, b3, 1, 0, 2, 0, 1), &t);
   // value | reward branch on the resident s' (Wh1 rows: actor 0..255, value 256..511, reward 512..767)
   t = job(3, 512, 0, 8, 0, 256, 1, bh1 + 512, 1, 4);         phase(0, job(3, 256, 0, 8, 0, 256, 0, bh1 + 256, 1, 0), &t);
   t = job(4, 0, 2, 4, 4, 256, 1, bb2 + 512, 1, 4);           phase(0, job(4, 0, 1, 4, 0, 256, 0, bb2 + 256, 1, 0), &t);
-  t = job(6, 0, 1, 4, 4, p3, 1, bb3 + p3, 0, -1, 0, 0, 2, 1);
-  phase(1, job(6, 0, 0, 4, 0, p3, 0, bb3, 0, -1, 0, 0, 2, 0), &t);
+  // the logits are staged in the (now idle) tile, K-blocks 0..3 / 4..7, and leave as bulk stores
+  t = job(6, 0, 1, 4, 4, p3, 1, bb3 + p3, 0, 4, 0, 0, 2, 1);
+  phase(1, job(6, 0, 0, 4, 0, p3, 0, bb3, 0, 0, 0, 0, 2, 0), &t);
   // policy branch on the reloaded s'
-  phase(0, job(3, 0, 0, 8, 0, 256, 0, bh1, 1, 0));                   // h  -> K-blocks 0..3
+  phase(0, job(3, 0, 0, 8, 0, 256, 0, bh1, 1, 0), nullptr, 1);       // h  -> K-blocks 0..3
   phase(0, job(4, 0, 0, 4, 0, 256, 1, bb2, 1, 4));                   // a1 -> K-blocks 4..7
   phase(0, job(5, 0, 0, 4, 4, 256, 0, ba2, 1, 0, 3, 0));             // a2 = relu(Wa2 a1 + h) -> K-blocks 0..3
-  phase(2, job(6, 0, 2, 4, 0, p3, 1, bb3 + 2 * p3, 0, -1, 0, 0, 2, 2));
+  phase(2, job(6, 0, 2, 4, 0, p3, 1, bb3 + 2 * p3, 0, 4, 0, 0, 2, 2));   // policy logits staged in K-blocks 4..7
   P.n_phases = np;
   P.rows = rows;
   P.row_blocks = (rows + kBM - 1) / kBM;
@@ -569,6 +624,11 @@ int hz_rowchain_destroy(hz_rowchain* e) {
 
 int hz_rowchain_set_state(hz_rowchain* e, void* state) {
   if (!e || !state || ((uintptr_t)state & 15)) { set_error("hz_rowchain_set_state: bad argument"); return HZ_ERR_ARG; }
+  if (state == (void*)e->params.state) return HZ_OK;
+  if (!make_w_map(&e->params.maps[kMapState], state, kF, e->params.rows, 1, kF, kBM)) {
+    set_error("hz_rowchain_set_state: cuTensorMapEncodeTiled failed");
+    return HZ_ERR_CUDA;
+  }
   e->params.state = (__half*)state;
   return HZ_OK;
 }
