@@ -21,6 +21,9 @@ import argparse
 import json
 import multiprocessing as mp
 import os
+# more than 8 searches in flight need more than the default 8 hardware work queues, or streams that share a queue
+# serialise (small root batches: 512 trees x 20 searches 47 -> 81 M simulations/s); must be set before CUDA starts
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import statistics
 import subprocess
 import sys
@@ -74,9 +77,10 @@ def parse_args():
                    help="SMs each in-flight search's library GEMMs are sized for (default: SearchPipeline's rule; 0 = whole device)")
     p.add_argument("--stage-limit", type=int, default=None,
                    help="hz_search_io.stage_limit of the in-flight searches (default: SearchPipeline's, 4; 0 = stage all that fits)")
-    p.add_argument("--executor", default="library", choices=["library", "rows"],
-                   help="network executor of the in-flight searches: seven cuBLASLt launches or the row-block resident kernel")
-    p.add_argument("--in-flight", type=int, default=8,
+    p.add_argument("--executor", default="auto", choices=["auto", "library", "rows"],
+                   help="network executor of the in-flight searches: seven cuBLASLt launches or the row-block resident "
+                        "kernel (auto = SearchPipeline's choice: rows when searches overlap)")
+    p.add_argument("--in-flight", type=int, default=None,
                    help="independent searches kept in flight per GPU (SearchPipeline depth); 1 = one search at a time")
     p.add_argument("--quick", action="store_true", help="search + roofline only (skip env / self-play / extras)")
     return p.parse_args()
@@ -481,11 +485,12 @@ class SearchBench:
         visits, _ = self.pipe.stats(self.pipe_ticket)
         return visits, (self.pipe.gathered(self.pipe_ticket) if self.pipe.gather is not None else None)
 
-    def search_step(self):
+    def search_step(self, executor="library", use_graph=None):
         """Roots.prepare + run_multi + root statistics (+ the statistics all_gather, off the compute stream)."""
         roots = self.cytree.Roots(self.n, self.A, self.S, device=self.dev)
         roots.prepare(CONST["frac"], self.noise, self.zeros_r, self.root_logits, self.legal_i)
-        self.mcts.run_multi(roots, self.model, self.root_hidden, use_graph=not self.args.no_graph)
+        self.mcts.run_multi(roots, self.model, self.root_hidden, executor=executor,
+                            use_graph=(not self.args.no_graph) if use_graph is None else use_graph)
         visits, values = roots.get_stats_tensors()
         if self.gather is not None:
             self.ticket = self.gather.submit(visits, values)
@@ -523,6 +528,10 @@ def run_ours(args):
     K, W = args.steps, max(args.warmup, 3)
     # searches in flight: at most --in-flight, lowered so that the K timed searches split into equally full waves (a ragged
     # last wave would run with fewer searches in flight than the figure claims)
+    if args.in_flight is None:
+        # a search is a chain of ~60-70 us steps whatever its size: small root batches (the shards of a strongly scaled
+        # job) need more searches in flight to fill the GPU than 4096-tree ones
+        args.in_flight = 8 if N >= 2048 else 20
     if args.in_flight > 1:
         waves = -(-K // args.in_flight)
         args.in_flight = max(1, -(-K // waves))
@@ -579,6 +588,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches_per_search = _lib.launch_count() - launches_before
     gemm_per_search = _lib.gemm_launch_count() - gemm_before
+    launches_one, gemm_one = launches_per_search, gemm_per_search
+    piped_executor = ("rows" if args.in_flight > 1 else "library") if args.executor == "auto" else args.executor
+    if args.in_flight > 1 and piped_executor == "rows":
+        # the timed searches run the network on the row-block resident executor: census of that path (eager, no graph)
+        launches_before, gemm_before = _lib.launch_count(), _lib.gemm_launch_count()
+        sb.search_step(executor="rows", use_graph=False)
+        torch.cuda.synchronize()
+        launches_per_search = _lib.launch_count() - launches_before
+        gemm_per_search = _lib.gemm_launch_count() - gemm_before
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -731,6 +749,9 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     roof = tree_roofline(torch, args, wl, sb, model, lib) if rank == 0 else None
+    net_roof = None
+    if rank == 0 and args.in_flight > 1 and piped_executor == "rows" and args.amp == "torch_amp":
+        net_roof = network_roofline(torch, args, wl, sb, model, lib)
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only) ----------------------------------------
     cpu = None
@@ -767,6 +788,7 @@ def run_ours(args):
                       "gemm_sm_target": (sb.pipe.gemm_sm_target if sb.pipe is not None else 0),
                       "tree_stage_limit": (sb.pipe.stage_limit if sb.pipe is not None else 0),
                       "network_executor": (sb.pipe.executor if sb.pipe is not None else "library"),
+                      "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                       "host_us_per_submit": (1e6 * sb.pipe.host_seconds / max(sb.pipe.submitted, 1) if sb.pipe is not None else None),
                       "what": f"`value` and `e2e` keep {max(args.in_flight, 1)} independent searches of the workload's root batch in "
                               "flight per GPU, each on its own stream (SearchPipeline: the reference's actors each own such a "
@@ -785,7 +807,8 @@ def run_ours(args):
             "gpu_launches": int(launches_per_search * K),
             "gpu_launches_per_search": int(launches_per_search),
             "library_gemm_launches_per_search": int(gemm_per_search),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "weak": weak, "plan_vs_module": agreement,
+            "launches_one_search_at_a_time": {"own": int(launches_one), "library_gemm": int(gemm_one)},
+            "clocks": clocks, "roofline": roof, "network_roofline": net_roof, "cpu_baseline": cpu, "weak": weak, "plan_vs_module": agreement,
             "env": env_obj, "selfplay": selfplay_obj,
         }
         print(json.dumps(line), flush=True)
@@ -980,6 +1003,78 @@ def measured_peak():
     if "hbm_gbs" in peaks:
         return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
+
+
+def network_roofline(torch, args, wl, sb, model, lib):
+    """Tensor roofline of the network executor the in-flight searches run (k_row_chain, hz_rowchain): algorithmic
+    FLOPs of one recurrent_inference (2 x in x out over the reference's Linear layers, the one-hot action columns
+    included, no padding) x rows per launch / launch duration, measured live with CUDA events two ways: D launches
+    in flight on D streams back to back (the regime the executor is built for: each launch holds rows/128 SMs), and
+    one launch after another on one stream (a launch alone leaves most SMs idle by design)."""
+    from hanabizero_b200.plan import BoundChain
+    plan = model.recurrent_plan(torch.float16)
+    N = wl["per_gpu"]
+    probe = BoundChain(plan, N)
+    if not probe.rows_supported():
+        return None
+    net = model
+    flops_row = 0
+    for m in net.modules():
+        if isinstance(m, torch.nn.Linear) and not any(m is x for x in net._representation.modules()):
+            flops_row += 2 * m.in_features * m.out_features
+    D = max(1, int(args.in_flight))
+    reps = 25
+    chains = [probe] + [BoundChain(plan, N) for _ in range(D - 1)]
+    for c in chains:
+        c.x0.copy_((torch.rand(c.x0.shape, device=c.x0.device) * 0.5).to(c.x0.dtype))
+        c.set_executor("rows")
+        c.bind_state(c.state)
+    streams = [torch.cuda.Stream() for _ in chains]
+    graphs = []
+    for c, st in zip(chains, streams):
+        with torch.cuda.stream(st):
+            c.run(st.cuda_stream)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                c.run(torch.cuda.current_stream().cuda_stream)
+        graphs.append(g)
+
+    def timed(n_streams):
+        e0 = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_streams)]
+        for st, g in list(zip(streams, graphs))[:n_streams]:
+            with torch.cuda.stream(st):
+                g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for st, g, e in list(zip(streams, graphs, ends))[:n_streams]:
+            st.wait_event(e0)
+            with torch.cuda.stream(st):
+                g.replay(); g.replay(); e.record(st)
+        torch.cuda.synchronize()
+        return max(e0.elapsed_time(e) for e in ends) * 1e-3 / (2 * reps * n_streams)    # seconds per launch, aggregate
+
+    t_flight, t_alone = timed(D), timed(1)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    src = "measured cuBLAS bf16, sustained (MEASURED_PEAKS.json)" if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    fl = flops_row * N
+    return {"bound": "tensor", "kernel": "k_row_chain (hz_rowchain_run): dynamics + reward/value/policy heads of one simulation, fp16 x fp16 -> fp32",
+            "achieved": fl / t_flight / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": fl / t_flight / 1e12 / peak,
+            "peak_source": src, "launches_in_flight": D, "launch_us_aggregate": t_flight * 1e6,
+            "algorithmic_flops_per_launch": fl, "algorithmic_flops_per_row": flops_row, "rows_per_launch": N,
+            "ctas_per_launch": -(-N // 128),
+            "alone": {"launch_us": t_alone * 1e6, "achieved": fl / t_alone / 1e12, "frac": fl / t_alone / 1e12 / peak,
+                      "what": "one launch after another on one stream: rows/128 CTAs busy, the other SMs idle (they are "
+                              "what the other searches in flight use)"},
+            "library_chain": "seven cuBLASLt launches of the same function: see profiles/r02_rowchain.md",
+            "traffic": None}
 
 
 def tree_roofline(torch, args, wl, sb, model, lib, stage_limit=None):

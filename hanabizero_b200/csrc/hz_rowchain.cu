@@ -51,12 +51,13 @@ struct RowJob {
   int32_t relu, dst_kb;                           // dst_kb >= 0: write fp16 into activation K-blocks dst_kb..
   int32_t res, res_off;                           // 0 none | 1 W1aT[action] + res_off | 2 x0 hidden + res_off | 3 activation K-block res_off
   int32_t gout, gb;                               // 0 none | 1 TMA-store the tile to `state` | 2 TMA-store K-blocks dst_kb.. to out[gb]
-  int32_t pad_;
+  int32_t kb1;                                    // MMA: K-blocks before this one need only the previous phase's FIRST job drained
   const __half* bias;
 };
 struct RowPhase {
   int32_t njobs, after;                           // after: 0 nothing | 1 reload s' | 2 load the next row block's s
-  int32_t a_wait, pad_;                           // the MMAs also wait for a TMA-loaded activation tile
+  int32_t a_wait, res_load;                       // the MMAs also wait for a TMA-loaded activation tile | the drain first
+                                                  // brings s back into the (consumed) tile as its residual
   RowJob job[2];
 };
 struct alignas(64) RowParams {
@@ -185,9 +186,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
   auto w_full = [&](int s) { return aux + 8u * s; };
   auto w_empty = [&](int s) { return aux + 8u * (kWSlots + s); };
   auto acc_full = [&](int h) { return aux + 8u * (2 * kWSlots + h); };
-  const uint32_t act_ready = aux + 8u * (2 * kWSlots + 2);
-  const uint32_t a_full = act_ready + 8u;       // a TMA-loaded activation tile (s, or s' coming back) has landed
-  const uint32_t tmem_slot = a_full + 8u;
+  // epilogue -> MMA, per phase: ready0 = the first job is drained (its TMEM half is free, its K-blocks of the tile are
+  // written), ready1 = the whole phase is (second job, stores, tile loads issued).  The next phase's first MMAs need
+  // ready0 only, so the second job's drain runs under them.
+  const uint32_t ready0 = aux + 8u * (2 * kWSlots + 2), ready1 = ready0 + 8u;
+  const uint32_t a_full = ready1 + 8u;          // a TMA-loaded activation tile (s, or s' coming back) has landed
+  const uint32_t res_full = a_full + 8u;        // ... the residual tile has landed (epilogue waits)
+  const uint32_t tmem_slot = res_full + 8u;
   const uint32_t sbias = aux + 128u;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
@@ -195,8 +200,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
     for (int s = 0; s < kWSlots; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     mbar_init(acc_full(0), 1);
     mbar_init(acc_full(1), 1);
-    mbar_init(act_ready, kEpiWarps);
+    mbar_init(ready0, kEpiWarps);
+    mbar_init(ready1, kEpiWarps);
     mbar_init(a_full, 1);
+    mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int m = 0; m < kMaps; ++m) tma_prefetch_desc(&P.maps[m]);
   }
@@ -236,18 +243,25 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const bool leader = elect_one();
-    uint32_t slot = 0, f_par = 0, ar_par = 0, af_par = 0;
+    uint32_t slot = 0, f_par = 0, r0_par = 0, r1_par = 0, af_par = 0;
     bool first_rb = true;
     for (int rb = blockIdx.x; rb < P.row_blocks; rb += gridDim.x) {
       for (int ph = 0; ph < P.n_phases; ++ph) {
         const RowPhase& F = P.phase[ph];
-        mbar_wait(act_ready, ar_par);        // the activation tile is written and both accumulators are drained
-        ar_par ^= 1u;
-        if (F.a_wait) {
-          mbar_wait(a_full, af_par);
-          af_par ^= 1u;
-        }
+        mbar_wait(ready0, r0_par);
+        r0_par ^= 1u;
         tc_fence_after();
+        bool got1 = false;
+        auto need_all = [&]() {              // everything the previous phase wrote, drained and loaded
+          mbar_wait(ready1, r1_par);
+          r1_par ^= 1u;
+          if (F.a_wait) {
+            mbar_wait(a_full, af_par);
+            af_par ^= 1u;
+          }
+          tc_fence_after();
+          got1 = true;
+        };
         if (leader && first_rb) stamp(P, ph, 0);
         for (int j = 0; j < F.njobs; ++j) {
           const RowJob& J = F.job[j];
@@ -255,6 +269,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
           const uint32_t idesc = (1u << 4) | ((uint32_t)(J.n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
           uint64_t da = umma_desc_k128(act + (uint32_t)J.a_kb * kKB);
           for (int kb = 0; kb < J.num_k; ++kb) {
+            if (!got1 && (j > 0 || kb >= J.kb1)) need_all();
             mbar_wait(w_full(slot), (f_par >> slot) & 1u);
             f_par ^= 1u << slot;
             tc_fence_after();
@@ -273,6 +288,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
           if (leader) tc_commit(acc_full(J.half));
           __syncwarp();
         }
+        if (!got1) need_all();
         if (leader && first_rb) stamp(P, ph, 1);
       }
       first_rb = false;
@@ -286,14 +302,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
     // all traffic between the activation tile and global memory is bulk-asynchronous and issued by ONE thread (et 0):
     // loads of s / s' complete on a_full, stores of s' and of the logits are bulk groups it waits for before the tile
     // is reused
-    auto load_tile = [&](int map, int rb_) {
-      mbar_expect_tx(a_full, kActBytes);
+    auto load_tile = [&](int map, int rb_, uint32_t bar) {
+      mbar_expect_tx(bar, kActBytes);
 #pragma unroll
-      for (int kb = 0; kb < kF / kBK; ++kb) tma_load_3d(act + kb * kKB, &P.maps[map], a_full, kb * kBK, rb_ * kBM, 0);
+      for (int kb = 0; kb < kF / kBK; ++kb) tma_load_3d(act + kb * kKB, &P.maps[map], bar, kb * kBK, rb_ * kBM, 0);
     };
-    if (et == 0) load_tile(kMapX0, blockIdx.x);
+    uint32_t rf_par = 0;
+    if (et == 0) load_tile(kMapX0, blockIdx.x, a_full);
     __syncwarp();
-    if (lane == 0) mbar_arrive(act_ready);
+    if (lane == 0) { mbar_arrive(ready0); mbar_arrive(ready1); }
     for (int rb = blockIdx.x; rb < P.row_blocks; rb += gridDim.x) {
       const int row = rb * kBM + rloc;
       const bool live = row < P.rows;
@@ -347,6 +364,13 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
         }
         tc_fence_after();
         if (et == 0 && first_rb) stamp(P, ph, 2);
+        if (F.res_load) {
+          // the tile has been consumed: the input state s comes back into it (bulk copy) and is read as the residual
+          // at shared-memory speed, in place (each thread reads a chunk of s before it writes the same chunk of s')
+          if (et == 0) load_tile(kMapX0, rb, res_full);
+          mbar_wait(res_full, rf_par);
+          rf_par ^= 1u;
+        }
         bool any_store = false;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -435,6 +459,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
               emit(rb2, eb0, eb1, c + 16);
             }
           }
+          if (j == 0) {   // the first job's half of TMEM and its K-blocks of the tile are ready for the next phase
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ready0);
+          }
         }
         if (any_store || F.after != 0) {
           // the tile (s', or the staged logits) goes out as bulk tensor stores; what comes in next follows them
@@ -457,10 +487,10 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
               tma_wait_all_but_last();
               tma_wait_read_all();
               asm volatile("fence.proxy.async;" ::: "memory");
-              load_tile(kMapState, rb);
+              load_tile(kMapState, rb, a_full);
             } else if (F.after == 2 && rb + (int)gridDim.x < P.row_blocks) {
               tma_wait_read_all();
-              load_tile(kMapX0, rb + gridDim.x);
+              load_tile(kMapX0, rb + gridDim.x, a_full);
             }
           }
         }
@@ -468,7 +498,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) k_row_chain(const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(act_ready);
+        if (lane == 0) mbar_arrive(ready1);
       }
       first_rb = false;
     }
@@ -582,8 +612,9 @@ int hz_rowchain_create(hz_rowchain** out, int device, const hz_rowchain_weights*
   // dynamics
   t = job(0, 256, 0, 8, 0, 256, 1, b1 + 256, 1, 4, 1, 256);  phase(0, job(0, 0, 0, 8, 0, 256, 0, b1, 1, 0, 1, 0), &t, 1);
   t = job(1, 256, 0, 8, 0, 256, 1, b2 + 256, 1, 4);          phase(0, job(1, 0, 0, 8, 0, 256, 0, b2, 1, 0), &t);
-  t = job(2, 256, 0, 8, 0, 256, 1, b3 + 256, 1, 4, 2, 256, 1);
-  phase(0, job(2, 0, 0, 8, 0, 256, 0, b3, 1, 0, 2, 0, 1), &t);
+  t = job(2, 256, 0, 8, 0, 256, 1, b3 + 256, 1, 4, 3, 4, 1);
+  phase(0, job(2, 0, 0, 8, 0, 256, 0, b3, 1, 0, 3, 0, 1), &t);
+  P.phase[np - 1].res_load = 1;                                      // + s, reloaded into the consumed tile
   // value | reward branch on the resident s' (Wh1 rows: actor 0..255, value 256..511, reward 512..767)
   t = job(3, 512, 0, 8, 0, 256, 1, bh1 + 512, 1, 4);         phase(0, job(3, 256, 0, 8, 0, 256, 0, bh1 + 256, 1, 0), &t);
   t = job(4, 0, 2, 4, 4, 256, 1, bb2 + 512, 1, 4);           phase(0, job(4, 0, 1, 4, 0, 256, 0, bb2 + 256, 1, 0), &t);
@@ -595,6 +626,20 @@ int hz_rowchain_create(hz_rowchain** out, int device, const hz_rowchain_weights*
   phase(0, job(4, 0, 0, 4, 0, 256, 1, bb2, 1, 4));                   // a1 -> K-blocks 4..7
   phase(0, job(5, 0, 0, 4, 4, 256, 0, ba2, 1, 0, 3, 0));             // a2 = relu(Wa2 a1 + h) -> K-blocks 0..3
   phase(2, job(6, 0, 2, 4, 0, p3, 1, bb3 + 2 * p3, 0, 4, 0, 0, 2, 2));   // policy logits staged in K-blocks 4..7
+  // how far a phase's first job may run on the previous phase's first job alone (see ready0 / ready1 in the kernel)
+  for (int p = 0; p < np; ++p) {
+    RowPhase& F = P.phase[p];
+    F.job[0].kb1 = 0;
+    F.job[1].kb1 = 0;
+    if (p == 0 || F.a_wait) continue;
+    const RowJob& A = P.phase[p - 1].job[0];
+    RowJob& J = F.job[0];
+    if (J.half != A.half || A.dst_kb < 0 || P.phase[p - 1].after != 0) continue;
+    const int w0 = (A.n + kBK - 1) / kBK;
+    int k = 0;
+    while (k < J.num_k && J.a_kb + k >= A.dst_kb && J.a_kb + k < A.dst_kb + w0) ++k;
+    J.kb1 = k;
+  }
   P.n_phases = np;
   P.rows = rows;
   P.row_blocks = (rows + kBM - 1) / kBM;

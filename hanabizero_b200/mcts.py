@@ -290,16 +290,23 @@ class SearchPipeline:
     `gathered(t)` returns them.  Weights must not change while searches are in flight: call drain() before updating
     the module.
 
-    Two settings make the slots share the GPU instead of queueing (profiles/r02_sm_target.md): `gemm_sm_target`
+    With depth > 1 the network runs on the row-block resident executor (`executor`, hz_rowchain: one launch per
+    simulation on n/128 SMs; profiles/r02_rowchain.md) where the plan supports it.  For the library chain two settings
+    make the slots share the GPU instead of queueing (profiles/r02_sm_target.md): `gemm_sm_target`
     (default gemm_sm_target_for(num_roots, depth)) sizes each search's library GEMMs for a share of the SMs, and
     `stage_limit` (default 4) keeps the tree step's shared-memory footprint small enough to sit next to a GEMM CTA.
     Results per search are those of MCTS.run_multi with the same two settings (the SM target changes the rounding of
     the network outputs in the last bits, the staging limit changes nothing)."""
 
     def __init__(self, mcts, model, num_roots, num_actions, depth=8, device=None, gather=None, gemm_sm_target=None,
-                 stage_limit=None, executor="library"):
+                 stage_limit=None, executor="auto"):
         self.mcts, self.model = mcts, model
-        self.executor = executor   # "rows": the network as one row-block resident launch (BoundChain.set_executor)
+        self.depth = int(depth)
+        # "rows": the network as one row-block resident launch per simulation (BoundChain.set_executor) — a quarter of
+        # the SMs per search at 4096 trees, which is what searches in flight want; "library": seven cuBLASLt launches,
+        # the lower latency for a search that runs alone.  "auto" = rows whenever searches overlap (plans the
+        # executor does not cover fall back to the library chain inside MCTS).
+        self.executor = ("rows" if self.depth > 1 else "library") if executor == "auto" else executor
         self.n, self.a, self.depth = int(num_roots), int(num_actions), int(depth)
         self.device = next(model.parameters()).device if device is None else torch.device(device)
         dev, sims = self.device, int(mcts.config.num_simulations)

@@ -116,6 +116,7 @@ class SelfPlayEngine:
         self._roots = None
         self.gemm_sm_target = 0      # SelfPlayPool sizes the search's GEMMs for a share of the SMs (mcts.gemm_sm_target_for)
         self.stage_limit = 0         # ... and shrinks the tree step's staging (hz_search_io.stage_limit)
+        self.executor = "library"    # ... and runs the network on the row-block resident executor (BoundChain.set_executor)
         if record:
             from .trajectory import TrajectoryRecorder
             self.recorder = TrajectoryRecorder(num_games, self.obs_dim, self.env.num_actions, self.stack,
@@ -196,7 +197,8 @@ class SelfPlayEngine:
             roots.prepare(cfg.root_exploration_fraction, nz, zeros, logits.float(), legal_i)
         else:
             roots.prepare_no_noise(zeros, logits.float(), legal_i)
-        self.mcts.run_multi(roots, self.model, hidden, gemm_sm_target=self.gemm_sm_target, stage_limit=self.stage_limit)
+        self.mcts.run_multi(roots, self.model, hidden, gemm_sm_target=self.gemm_sm_target, stage_limit=self.stage_limit,
+                            executor=self.executor)
         self.moves += 1
         visits, values = roots.get_stats_tensors()
         actions, entropy = select_action_batch(visits, self.legal, temperature, deterministic)
@@ -253,6 +255,7 @@ class SelfPlayPool:
         for eng in self.engines:
             eng.gemm_sm_target = gemm_sm_target_for(eng.n, len(self.engines), dev)
             eng.stage_limit = STAGE_LIMIT_IN_FLIGHT if len(self.engines) > 1 else 0
+            eng.executor = "rows" if len(self.engines) > 1 else "library"
         cur = torch.cuda.current_stream(dev)
         for s in self.streams:
             s.wait_stream(cur)       # engine construction ran on the caller's stream

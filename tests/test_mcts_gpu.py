@@ -259,7 +259,8 @@ def test_search_pipeline_equals_serial_searches(depth, on_device):
             roots.prepare_no_noise(j["reward"], j["logits"], j["legal"])
         else:
             roots.prepare(0.25, j["noise"], j["reward"], j["logits"], j["legal"])
-        ref.run_multi(roots, model, j["hidden"], gemm_sm_target=pipe.gemm_sm_target)   # same library kernels => same roundings
+        ref.run_multi(roots, model, j["hidden"], gemm_sm_target=pipe.gemm_sm_target,
+                      executor=pipe.executor)                      # same network kernels => same roundings
         v, val = roots.get_stats_tensors()
         assert torch.equal(v.cpu(), j["visits"].cpu()) and torch.equal(val.cpu(), j["values"].cpu())
         assert int(j["visits"].sum()) == N * (S - 1)

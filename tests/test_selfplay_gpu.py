@@ -231,7 +231,8 @@ def test_selfplay_pool_equals_its_engines_stepped_alone():
     alone = []
     for e in range(E):
         eng = make(e)
-        eng.gemm_sm_target = gemm_sm_target_for(N, E, dev)     # the pool's choice of library kernels => same roundings
+        eng.gemm_sm_target = gemm_sm_target_for(N, E, dev)     # the pool's choice of network kernels => same roundings
+        eng.executor = "rows"                                  # (engines in a pool run the row-block resident executor)
         eng.reset()
         alone.append([{k: v.clone() for k, v in eng.step(deterministic=True).items()} for _ in range(moves)])
     torch.cuda.synchronize()
