@@ -485,8 +485,11 @@ class SearchBench:
         visits, _ = self.pipe.stats(self.pipe_ticket)
         return visits, (self.pipe.gathered(self.pipe_ticket) if self.pipe.gather is not None else None)
 
-    def search_step(self, executor="library", use_graph=None):
-        """Roots.prepare + run_multi + root statistics (+ the statistics all_gather, off the compute stream)."""
+    def search_step(self, executor=None, use_graph=None):
+        """Roots.prepare + run_multi + root statistics (+ the statistics all_gather, off the compute stream).  One search
+        at a time runs the library chain (its lower latency) unless --executor rows asks otherwise."""
+        if executor is None:
+            executor = "rows" if self.args.executor == "rows" else "library"
         roots = self.cytree.Roots(self.n, self.A, self.S, device=self.dev)
         roots.prepare(CONST["frac"], self.noise, self.zeros_r, self.root_logits, self.legal_i)
         self.mcts.run_multi(roots, self.model, self.root_hidden, executor=executor,
@@ -531,7 +534,7 @@ def run_ours(args):
     if args.in_flight is None:
         # a search is a chain of ~60-70 us steps whatever its size: small root batches (the shards of a strongly scaled
         # job) need more searches in flight to fill the GPU than 4096-tree ones
-        args.in_flight = 8 if N >= 2048 else 20
+        args.in_flight = 8 if N >= 3072 else 20
     if args.in_flight > 1:
         waves = -(-K // args.in_flight)
         args.in_flight = max(1, -(-K // waves))
@@ -706,6 +709,15 @@ def run_ours(args):
         # the two paths are the same function up to the rounding of the network (fp16 storage, BN folding, library kernels)
         assert agreement["root_action_agreement"] >= 0.99 or wl["config"] != 4 or N < 4096, \
             f"production path picks a different root action on {1 - agreement['root_action_agreement']:.1%} of the trees"
+        if pipe.executor == "rows":
+            # the searches in flight run the network on the row-block resident executor: same inputs, its own roundings
+            vr, valr = h_out[0][0].to(dev), h_out[0][1].to(dev)
+            agreement["rows_executor"] = {
+                "root_action_agreement_with_module": float((vm.argmax(1) == vr.argmax(1)).float().mean()),
+                "root_action_agreement_with_library_chain": float((vp.argmax(1) == vr.argmax(1)).float().mean()),
+                "root_value_max_abs_diff_with_module": float((valm - valr).abs().max())}
+            assert agreement["rows_executor"]["root_action_agreement_with_module"] >= 0.99 or wl["config"] != 4 or N < 4096, \
+                "row-block executor path picks different root actions"
 
     env_obj, selfplay_obj = None, None
     if not args.quick:
