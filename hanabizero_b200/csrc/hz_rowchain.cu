@@ -16,13 +16,21 @@
 //
 //   warp 0      TMA producer: weight tiles [256 (or 208) out-columns x 64 k] in the static order of the job table
 //   warp 1      tcgen05.mma issuer (one lane), M = 128, N = 256 | 208, K = 16, fp16 x fp16 -> fp32 in TMEM
-//   warps 2-17  epilogue: tcgen05.ld -> + bias (+ residual) -> ReLU -> fp16 -> activation tile (swizzled) or global
+//   warps 2-17  epilogue: tcgen05.ld -> + bias (+ residual) -> ReLU -> fp16 -> back into the activation tile (swizzled),
+//               in place; one of its threads moves whole tiles between shared and global memory as bulk tensor copies
+//               (s in, s' out to the pool and back in for the policy branch, logits out)
+//
+// A launch runs ten phases (the job table hz_rowchain_create builds): fc1 | fc2 | fc3 + s | value, reward first layers |
+// their second layers | their logits | policy h | a1 | a2 | policy logits.  A phase = one or two jobs (one per TMEM
+// half) of MMAs, then their drains; the next phase's first MMAs start as soon as the first job is drained (ready0).
 //
 // The one-hot action columns of fc1 are not multiplied: row r adds column a_r of W1's action block (a 32 x 512 table,
-// W1aT) in the epilogue, which is the same sum.  The value/reward branch runs first on the resident s'; the policy
-// branch re-reads s' (already stored to the pool) afterwards, because three 256-wide first layers do not fit TMEM.
+// W1aT) in the epilogue, which is the same sum.  fc3's residual s is copied back into the consumed tile and read from
+// shared memory.  The value/reward branch runs first on the resident s'; the policy branch re-reads s' (already stored
+// to the pool) afterwards, because three 256-wide first layers need 768 TMEM columns.
 //
 // fp16 plans of the Hanabi-Full network only (F = 512, H = 256); everything else stays on the library chain.
+// Measurements, stamps and what bounds it: profiles/r02_rowchain.md.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -49,7 +57,7 @@ constexpr unsigned kSpin = 1u << 26;               // a stuck wait traps instead
 struct RowJob {
   int32_t map, n0, batch, num_k, a_kb, n, half;   // weight tile source, A K-block offset, MMA N, TMEM half
   int32_t relu, dst_kb;                           // dst_kb >= 0: write fp16 into activation K-blocks dst_kb..
-  int32_t res, res_off;                           // 0 none | 1 W1aT[action] + res_off | 2 x0 hidden + res_off | 3 activation K-block res_off
+  int32_t res, res_off;                           // 0 none | 1 W1aT[action] + res_off | 2 x0 hidden + res_off (global) | 3 tile K-block res_off
   int32_t gout, gb;                               // 0 none | 1 TMA-store the tile to `state` | 2 TMA-store K-blocks dst_kb.. to out[gb]
   int32_t kb1;                                    // MMA: K-blocks before this one need only the previous phase's FIRST job drained
   const __half* bias;
