@@ -534,7 +534,8 @@ def run_ours(args):
     if args.in_flight is None:
         # a search is a chain of ~60-70 us steps whatever its size: small root batches (the shards of a strongly scaled
         # job) need more searches in flight to fill the GPU than 4096-tree ones
-        args.in_flight = 8 if N >= 3072 else 20
+        rows_ok = wl["game"] == "Hanabi-Full" and args.amp == "torch_amp" and args.executor != "library"
+        args.in_flight = 20 if (N < 3072 and rows_ok) else 8
     if args.in_flight > 1:
         waves = -(-K // args.in_flight)
         args.in_flight = max(1, -(-K // waves))
