@@ -800,7 +800,8 @@ def run_ours(args):
                       "searches_in_flight": max(args.in_flight, 1),
                       "gemm_sm_target": (sb.pipe.gemm_sm_target if sb.pipe is not None else 0),
                       "tree_stage_limit": (sb.pipe.stage_limit if sb.pipe is not None else 0),
-                      "network_executor": (sb.pipe.executor if sb.pipe is not None else "library"),
+                      "network_executor": ("rows" if any(getattr(w, "chain", None) is not None and w.chain._use_rows
+                                                         for w in sb.mcts._ws.values()) else "library"),
                       "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
                       "host_us_per_submit": (1e6 * sb.pipe.host_seconds / max(sb.pipe.submitted, 1) if sb.pipe is not None else None),
                       "what": f"`value` and `e2e` keep {max(args.in_flight, 1)} independent searches of the workload's root batch in "
